@@ -1,0 +1,433 @@
+// api.cu -- the extern "C" layer of include/llcomp_b200.h: per-device context, stream containers,
+// host-buffer and device-resident entry points.  Replaces the call sites llcompc.cpp:33
+// (compressImage) and llcompd.cpp:26 (decompressImage) of the reference; header layout follows
+// llcomp.hpp:375-378 / :463-470.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/llcomp_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace llc;
+
+namespace {
+
+enum Stage { kStFrontend = 0, kStCoder, kStScan, kStCompact, kStDecoder };
+const char* const kStageNames[LLCOMP_B200_N_STAGES] = {"frontend", "slice_coder", "scan", "compact", "slice_decoder"};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct llcomp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;          // used by the host-buffer entry points
+    DevBuf<uint32_t> sym;                   // K1 -> K2 records
+    DevBuf<uint8_t> scratch;                // K2 per-slice payloads before compaction
+    DevBuf<uint32_t> slice_bytes;
+    DevBuf<int16_t> lines;                  // K5 row scratch when a tile row does not fit in smem
+    DevBuf<uint8_t> pixels, payload;        // staging of the host-buffer entry points
+    DevBuf<uint64_t> offsets;
+    int* d_status = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[LLCOMP_B200_N_STAGES + 1] = {};
+    bool ev_made = false;
+    int ev_first = -1, ev_last = -1;        // stages recorded by the last device call
+};
+
+namespace {
+
+int fail_cuda(llcomp_ctx* c, cudaError_t e, const char* where) {
+    if (c) c->last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? LLCOMP_ERR_NOMEM : LLCOMP_ERR_CUDA;
+}
+#define CK(call)                                                    \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);    \
+    } while (0)
+
+bool make_geom(const llcomp_geometry* in, Geom* g) {
+    if (!in) return false;
+    if (in->width < 1 || in->height < 1 || in->channels < 1 || in->channels > 255 || in->n_images < 1) return false;
+    if (in->tile_w < 0 || in->tile_h < 0) return false;
+    g->W = in->width; g->H = in->height; g->C = in->channels; g->n_images = in->n_images;
+    g->tw = (in->tile_w == 0 || in->tile_w > in->width) ? in->width : in->tile_w;
+    g->th = (in->tile_h == 0 || in->tile_h > in->height) ? in->height : in->tile_h;
+    g->tiles_x = (g->W + g->tw - 1) / g->tw;
+    g->tiles_y = (g->H + g->th - 1) / g->th;
+    if ((uint64_t)g->tw * g->th * g->C >= (1ull << 30)) return false;   // per-slice byte counts are u32
+    if (g->n_slices() >= (1ull << 31)) return false;
+    return true;
+}
+
+uint64_t payload_capacity(const Geom& g) { return 2 * g.n_samples() + kScratchSlack * g.n_slices(); }
+
+void put_u32(uint8_t* p, uint32_t v) { p[0] = v & 0xFF; p[1] = (v >> 8) & 0xFF; p[2] = (v >> 16) & 0xFF; p[3] = v >> 24; }
+uint32_t get_u32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// A single-slice image that fits u16 dimensions is written in the reference's own format.
+bool is_reference_layout(const Geom& g) { return g.slices_per_image() == 1 && g.W <= 0xFFFF && g.H <= 0xFFFF; }
+size_t header_bytes(const Geom& g) { return is_reference_layout(g) ? 6 : 24 + 4 * (size_t)g.slices_per_image(); }
+
+void write_header(const Geom& g, const uint64_t* off /* offsets of this image's slices, spi+1 */, uint8_t* h) {
+    if (is_reference_layout(g)) {                        // llcomp.hpp:375-378
+        h[0] = LLCOMP_MAGIC_REV2; h[1] = (uint8_t)g.C;
+        h[2] = g.W & 0xFF; h[3] = (g.W >> 8) & 0xFF;
+        h[4] = g.H & 0xFF; h[5] = (g.H >> 8) & 0xFF;
+        return;
+    }
+    const uint32_t spi = g.slices_per_image();
+    h[0] = LLCOMP_MAGIC_SLICED; h[1] = 1; h[2] = (uint8_t)g.C; h[3] = 0;
+    put_u32(h + 4, g.W); put_u32(h + 8, g.H); put_u32(h + 12, g.tw); put_u32(h + 16, g.th); put_u32(h + 20, spi);
+    for (uint32_t k = 0; k < spi; ++k) put_u32(h + 24 + 4 * k, (uint32_t)(off[k + 1] - off[k]));
+}
+
+// Parses either header.  lens receives the per-slice payload byte counts (reference stream: one entry).
+int parse_header(const uint8_t* s, size_t n, llcomp_geometry* g, size_t* hdr, std::vector<uint32_t>* lens) {
+    if (!s || n < 1) return LLCOMP_ERR_BAD_ARG;
+    if (s[0] == LLCOMP_MAGIC_REV2) {                     // llcomp.hpp:463-470
+        if (n < 6) return LLCOMP_ERR_TRUNCATED;
+        g->channels = s[1];
+        g->width = s[2] | (s[3] << 8);
+        g->height = s[4] | (s[5] << 8);
+        g->tile_w = g->width; g->tile_h = g->height; g->n_images = 1;
+        *hdr = 6;
+        if (lens) lens->assign(1, (uint32_t)std::min<size_t>(n - 6, 0xFFFFFFFFu));
+        return LLCOMP_OK;
+    }
+    if (s[0] != LLCOMP_MAGIC_SLICED) return LLCOMP_ERR_BAD_MAGIC;
+    if (n < 24) return LLCOMP_ERR_TRUNCATED;
+    if (s[1] != 1) return LLCOMP_ERR_BAD_MAGIC;
+    g->channels = s[2];
+    g->width = (int32_t)get_u32(s + 4); g->height = (int32_t)get_u32(s + 8);
+    g->tile_w = (int32_t)get_u32(s + 12); g->tile_h = (int32_t)get_u32(s + 16);
+    g->n_images = 1;
+    const uint32_t spi = get_u32(s + 20);
+    Geom gg;
+    if (g->width < 1 || g->height < 1 || g->tile_w < 1 || g->tile_h < 1 || !make_geom(g, &gg)) return LLCOMP_ERR_BAD_ARG;
+    if (gg.slices_per_image() != spi || gg.tw != g->tile_w || gg.th != g->tile_h) return LLCOMP_ERR_BAD_ARG;
+    if (n < 24 + 4 * (size_t)spi) return LLCOMP_ERR_TRUNCATED;
+    *hdr = 24 + 4 * (size_t)spi;
+    if (lens) {
+        lens->resize(spi);
+        for (uint32_t k = 0; k < spi; ++k) (*lens)[k] = get_u32(s + 24 + 4 * k);
+    }
+    return LLCOMP_OK;
+}
+
+void begin_stages(llcomp_ctx* ctx, cudaStream_t st, int first) {
+    ctx->ev_first = ctx->ev_last = -1;
+    if (!ctx->profiling) return;
+    if (!ctx->ev_made) {
+        for (auto& e : ctx->ev) cudaEventCreate(&e);
+        ctx->ev_made = true;
+    }
+    cudaEventRecord(ctx->ev[first], st);
+    ctx->ev_first = first;
+}
+void end_stage(llcomp_ctx* ctx, cudaStream_t st, int stage) {
+    ctx->launches++;
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->ev[stage + 1], st);
+    ctx->ev_last = stage;
+}
+
+}  // namespace
+
+extern "C" {
+
+int llcomp_b200_abi_version(void) { return LLCOMP_B200_ABI_VERSION; }
+
+const char* llcomp_b200_status_string(int s) {
+    switch (s) {
+        case LLCOMP_OK: return "ok";
+        case LLCOMP_ERR_BAD_MAGIC: return "Invalid magic number";     // llcomp.hpp:466
+        case LLCOMP_ERR_BAD_EXPONENT: return "Invalid exponent";      // llcomp.hpp:233
+        case LLCOMP_ERR_BAD_ARG: return "bad argument";
+        case LLCOMP_ERR_NOMEM: return "out of memory";
+        case LLCOMP_ERR_OVERFLOW: return "slice payload exceeds its buffer";
+        case LLCOMP_ERR_CUDA: return "CUDA error";
+        case LLCOMP_ERR_TRUNCATED: return "truncated container header";
+        default: return "unknown status";
+    }
+}
+
+const char* llcomp_b200_last_error(const llcomp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+const char* llcomp_b200_stage_name(int i) { return (i >= 0 && i < LLCOMP_B200_N_STAGES) ? kStageNames[i] : ""; }
+
+int llcomp_b200_ctx_create(int device, llcomp_ctx** out) {
+    if (!out) return LLCOMP_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        (void)cudaGetLastError();
+        return LLCOMP_ERR_CUDA;                                      // no device: there is no CPU fallback
+    }
+    llcomp_ctx* ctx = new (std::nothrow) llcomp_ctx;
+    if (!ctx) return LLCOMP_ERR_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int));
+    if (e == cudaSuccess) e = configure_slice_coder();
+    if (e == cudaSuccess) e = configure_slice_decoder();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "llcomp_b200: context creation failed: %s\n", cudaGetErrorString(e));
+        llcomp_b200_ctx_destroy(ctx);
+        return LLCOMP_ERR_CUDA;
+    }
+    *out = ctx;
+    return LLCOMP_OK;
+}
+
+void llcomp_b200_ctx_destroy(llcomp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->sym.release(); ctx->scratch.release(); ctx->slice_bytes.release(); ctx->lines.release();
+    ctx->pixels.release(); ctx->payload.release(); ctx->offsets.release();
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->ev_made) for (auto& e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+uint64_t llcomp_b200_slice_count(const llcomp_geometry* g) { Geom gg; return make_geom(g, &gg) ? gg.n_slices() : 0; }
+uint64_t llcomp_b200_sample_count(const llcomp_geometry* g) { Geom gg; return make_geom(g, &gg) ? gg.n_samples() : 0; }
+uint64_t llcomp_b200_payload_capacity(const llcomp_geometry* g) { Geom gg; return make_geom(g, &gg) ? payload_capacity(gg) : 0; }
+uint64_t llcomp_b200_stream_bound(const llcomp_geometry* g) {
+    Geom gg;
+    if (!make_geom(g, &gg)) return 0;
+    return payload_capacity(gg) + (uint64_t)header_bytes(gg) * gg.n_images;
+}
+uint64_t llcomp_b200_launch_count(const llcomp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void llcomp_b200_set_profiling(llcomp_ctx* ctx, int on) { if (ctx) ctx->profiling = on != 0; }
+
+int llcomp_b200_stage_times(llcomp_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return LLCOMP_ERR_BAD_ARG;
+    for (int i = 0; i < LLCOMP_B200_N_STAGES; ++i) ms[i] = 0.f;
+    if (!ctx->profiling || ctx->ev_first < 0) return LLCOMP_OK;
+    CK(cudaEventSynchronize(ctx->ev[ctx->ev_last + 1]));
+    for (int i = ctx->ev_first; i <= ctx->ev_last; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return LLCOMP_OK;
+}
+
+// ---- device-resident path --------------------------------------------------------------------
+int llcomp_b200_frontend_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const llcomp_geometry* gi, uint32_t* d_sym,
+                                void* cuda_stream) {
+    Geom g;
+    if (!ctx || !d_pixels || !d_sym || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    begin_stages(ctx, st, kStFrontend);
+    CK(launch_frontend(d_pixels, g, d_sym, st));
+    end_stage(ctx, st, kStFrontend);
+    return LLCOMP_OK;
+}
+
+int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const llcomp_geometry* gi, uint8_t* d_payload,
+                              uint64_t capacity, uint64_t* d_offsets, void* cuda_stream) {
+    Geom g;
+    if (!ctx || !d_pixels || !d_payload || !d_offsets || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CK(ctx->sym.reserve(g.n_samples()));
+    CK(ctx->scratch.reserve(payload_capacity(g) + 64));
+    CK(ctx->slice_bytes.reserve(g.n_slices()));
+
+    begin_stages(ctx, st, kStFrontend);
+    CK(launch_frontend(d_pixels, g, ctx->sym.p, st));
+    end_stage(ctx, st, kStFrontend);
+    CK(launch_slice_coder(ctx->sym.p, g, ctx->scratch.p, ctx->slice_bytes.p, ctx->d_status, st));
+    end_stage(ctx, st, kStCoder);
+    CK(launch_scan(ctx->slice_bytes.p, g.n_slices(), d_offsets, capacity, ctx->d_status, st));
+    end_stage(ctx, st, kStScan);
+    CK(launch_compact(ctx->scratch.p, g, d_offsets, d_payload, capacity, st));
+    end_stage(ctx, st, kStCompact);
+    return LLCOMP_OK;
+}
+
+int llcomp_b200_decode_device(llcomp_ctx* ctx, const uint8_t* d_payload, const uint64_t* d_offsets,
+                              const llcomp_geometry* gi, uint8_t* d_pixels, void* cuda_stream) {
+    Geom g;
+    if (!ctx || !d_payload || !d_offsets || !d_pixels || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const uint64_t lb = decoder_line_scratch_bytes(g);
+    if (lb) CK(ctx->lines.reserve(lb / 2));
+    begin_stages(ctx, st, kStDecoder);
+    CK(launch_slice_decoder(d_payload, d_offsets, g, d_pixels, ctx->lines.p, ctx->d_status, st));
+    end_stage(ctx, st, kStDecoder);
+    return LLCOMP_OK;
+}
+
+int llcomp_b200_finish(llcomp_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return LLCOMP_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    int st = 0;
+    CK(cudaMemcpy(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != 0) CK(cudaMemset(ctx->d_status, 0, sizeof(int)));
+    return st;
+}
+
+// ---- host-buffer path ------------------------------------------------------------------------
+int llcomp_b200_encode_batch(llcomp_ctx* ctx, const uint8_t* pixels, const llcomp_geometry* gi, uint8_t* out,
+                             uint64_t out_cap, uint64_t* offsets) {
+    Geom g;
+    if (!ctx || !pixels || !out || !offsets || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t ns = g.n_slices(), cap = payload_capacity(g);
+    const uint32_t spi = g.slices_per_image();
+    CK(ctx->pixels.reserve(g.n_samples()));
+    CK(ctx->payload.reserve(cap));
+    CK(ctx->offsets.reserve(ns + 1));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->pixels.p, pixels, g.n_samples(), cudaMemcpyHostToDevice, st));
+    int rc = llcomp_b200_encode_device(ctx, ctx->pixels.p, gi, ctx->payload.p, cap, ctx->offsets.p, st);
+    if (rc) return rc;
+    std::vector<uint64_t> off(ns + 1);
+    CK(cudaMemcpyAsync(off.data(), ctx->offsets.p, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    rc = llcomp_b200_finish(ctx, st);
+    if (rc) return rc;
+
+    const size_t hb = header_bytes(g);
+    uint64_t pos = 0;
+    for (int k = 0; k < g.n_images; ++k) {
+        const uint64_t p0 = off[(uint64_t)k * spi], p1 = off[(uint64_t)(k + 1) * spi];
+        offsets[k] = pos;
+        if (pos + hb + (p1 - p0) > out_cap) return LLCOMP_ERR_OVERFLOW;
+        write_header(g, &off[(uint64_t)k * spi], out + pos);
+        CK(cudaMemcpyAsync(out + pos + hb, ctx->payload.p + p0, p1 - p0, cudaMemcpyDeviceToHost, st));
+        pos += hb + (p1 - p0);
+    }
+    offsets[g.n_images] = pos;
+    CK(cudaStreamSynchronize(st));
+    return LLCOMP_OK;
+}
+
+int llcomp_b200_encode(llcomp_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, int tile_w,
+                       int tile_h, uint8_t** stream, size_t* stream_len) {
+    if (!stream || !stream_len) return LLCOMP_ERR_BAD_ARG;
+    *stream = nullptr; *stream_len = 0;
+    llcomp_geometry gi = {width, height, channels, tile_w, tile_h, 1};
+    const uint64_t bound = llcomp_b200_stream_bound(&gi);
+    if (!bound) return LLCOMP_ERR_BAD_ARG;
+    uint8_t* buf = static_cast<uint8_t*>(malloc(bound));
+    if (!buf) return LLCOMP_ERR_NOMEM;
+    uint64_t off[2];
+    const int rc = llcomp_b200_encode_batch(ctx, pixels, &gi, buf, bound, off);
+    if (rc) { free(buf); return rc; }
+    uint8_t* fit = static_cast<uint8_t*>(realloc(buf, off[1] ? off[1] : 1));
+    *stream = fit ? fit : buf;
+    *stream_len = off[1];
+    return LLCOMP_OK;
+}
+
+int llcomp_b200_peek(const uint8_t* stream, size_t n, int* w, int* h, int* c, int* tw, int* th) {
+    llcomp_geometry g; size_t hdr;
+    const int rc = parse_header(stream, n, &g, &hdr, nullptr);
+    if (rc) return rc;
+    if (w) *w = g.width; if (h) *h = g.height; if (c) *c = g.channels;
+    if (tw) *tw = g.tile_w; if (th) *th = g.tile_h;
+    return LLCOMP_OK;
+}
+
+int llcomp_b200_decode_batch(llcomp_ctx* ctx, const uint8_t* streams, const uint64_t* offsets, int n_images,
+                             uint8_t* pixels_out, uint64_t pixels_cap, llcomp_geometry* g_out) {
+    if (!ctx || !streams || !offsets || n_images < 1 || !pixels_out) return LLCOMP_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    llcomp_geometry gi{};
+    std::vector<uint64_t> off;          // slice offsets inside the contiguous device payload
+    std::vector<uint32_t> lens;
+    struct Piece { uint64_t src, dst, n; };
+    std::vector<Piece> pieces;          // host byte ranges that exist (the rest reads as zero, llcomp.hpp:476-477)
+    uint64_t total = 0;
+    off.push_back(0);
+    for (int k = 0; k < n_images; ++k) {
+        const uint8_t* s = streams + offsets[k];
+        const size_t n = (size_t)(offsets[k + 1] - offsets[k]);
+        llcomp_geometry gk; size_t hdr;
+        const int rc = parse_header(s, n, &gk, &hdr, &lens);
+        if (rc) return rc;
+        if (k == 0) gi = gk;
+        else if (gk.width != gi.width || gk.height != gi.height || gk.channels != gi.channels ||
+                 gk.tile_w != gi.tile_w || gk.tile_h != gi.tile_h) return LLCOMP_ERR_BAD_ARG;
+        uint64_t want = 0;
+        for (uint32_t L : lens) { want += L; off.push_back(total + want); }
+        const uint64_t have = std::min<uint64_t>(want, n - hdr);
+        if (have) pieces.push_back({offsets[k] + hdr, total, have});
+        total += want;
+    }
+    gi.n_images = n_images;
+    if (gi.width == 0 || gi.height == 0 || gi.channels == 0) {   // empty image: nothing to decode
+        if (g_out) *g_out = gi;
+        return LLCOMP_OK;
+    }
+    Geom g;
+    if (!make_geom(&gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    if (g.n_samples() > pixels_cap) return LLCOMP_ERR_OVERFLOW;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->payload.reserve(total + 16));
+    CK(ctx->offsets.reserve(off.size()));
+    CK(ctx->pixels.reserve(g.n_samples()));
+    CK(cudaMemsetAsync(ctx->payload.p, 0, total + 16, st));
+    for (const Piece& p : pieces)
+        CK(cudaMemcpyAsync(ctx->payload.p + p.dst, streams + p.src, p.n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->offsets.p, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    int rc = llcomp_b200_decode_device(ctx, ctx->payload.p, ctx->offsets.p, &gi, ctx->pixels.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(pixels_out, ctx->pixels.p, g.n_samples(), cudaMemcpyDeviceToHost, st));
+    rc = llcomp_b200_finish(ctx, st);
+    if (rc) return rc;
+    if (g_out) *g_out = gi;
+    return LLCOMP_OK;
+}
+
+int llcomp_b200_decode(llcomp_ctx* ctx, const uint8_t* stream, size_t n, uint8_t** pixels, int* w, int* h, int* c) {
+    if (!pixels || !w || !h || !c) return LLCOMP_ERR_BAD_ARG;
+    *pixels = nullptr;
+    llcomp_geometry g; size_t hdr;
+    int rc = parse_header(stream, n, &g, &hdr, nullptr);
+    if (rc) return rc;
+    const uint64_t bytes = (uint64_t)g.width * g.height * g.channels;
+    uint8_t* buf = static_cast<uint8_t*>(malloc(bytes ? bytes : 1));
+    if (!buf) return LLCOMP_ERR_NOMEM;
+    const uint64_t off[2] = {0, n};
+    rc = llcomp_b200_decode_batch(ctx, stream, off, 1, buf, bytes, &g);
+    if (rc) { free(buf); return rc; }
+    *pixels = buf; *w = g.width; *h = g.height; *c = g.channels;
+    return LLCOMP_OK;
+}
+
+void llcomp_b200_free(void* p) { free(p); }
+
+// Model table entry s: P | next_mps<<8 | next_lps<<16 (tests compare it with the oracle's tables).
+uint32_t llcomp_b200_debug_table(int s) {
+    static const ModelTables t = make_tables();
+    return (s >= 0 && s < 128) ? t.entry[s] : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI (llcomp_b200.Codec -> ctypes ->
+libllcomp_b200.so).  Bit-exact everywhere: this is integer/byte work.
+
+Mirrors the test list of SURVEY.md section 4: known answers, differential vs the reference semantics,
+round trips, tail padding, carry propagation, plus size-independent properties at BASELINE sizes.
+"""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import llcomp_b200
+    return llcomp_b200.default_codec(0)
+
+
+def split_container(stream: bytes):
+    """(w, h, c, tile_w, tile_h, [payload per slice]) of either stream layout."""
+    if stream[0] == 0x79:
+        c, w, h = stream[1], stream[2] | stream[3] << 8, stream[4] | stream[5] << 8
+        return w, h, c, w, h, [stream[6:]]
+    assert stream[0] == 0xB2 and stream[1] == 1
+    c = stream[2]
+    w, h, tw, th, n = struct.unpack_from("<5I", stream, 4)
+    lens = struct.unpack_from(f"<{n}I", stream, 24)
+    pos, out = 24 + 4 * n, []
+    for L in lens:
+        out.append(stream[pos:pos + L])
+        pos += L
+    assert pos == len(stream)
+    return w, h, c, tw, th, out
+
+
+def tiles_of(w, h, tw, th):
+    return [(x0, y0, min(tw, w - x0), min(th, h - y0)) for y0 in range(0, h, th) for x0 in range(0, w, tw)]
+
+
+def rand_image(rng, w, h, c, amp):
+    base = (np.add.outer(np.arange(h) * 2, np.arange(w) * 3)[:, :, None] + np.arange(c) * 23) % 256
+    noise = rng.integers(-amp, amp + 1, size=(h, w, c)) if amp else 0
+    return np.clip(base + noise, 0, 255).astype(np.uint8)
+
+
+# ---- known answers ----------------------------------------------------------------------------
+def test_kat_streams_byte_identical(codec, kats):
+    for name, px, stream in kats:
+        h, w, c = px.shape
+        assert codec.compress(px, w, h, c) == stream, name
+
+
+def test_kat_decode(codec, kats):
+    for name, px, stream in kats:
+        img = codec.decompress(stream)
+        assert (img.width, img.height, img.channels) == (px.shape[1], px.shape[0], px.shape[2]), name
+        assert (img.pixels == px).all(), name
+
+
+def test_small_fixtures(codec):
+    with open(os.path.join(GOLDEN, "small_fixtures.json")) as f:
+        fx = json.load(f)["fixtures"]
+    for x in fx:
+        px = np.array(x["pixels"], dtype=np.uint8).reshape(x["h"], x["w"], x["c"])
+        s = bytes.fromhex(x["stream"])
+        assert codec.compress(px, x["w"], x["h"], x["c"]) == s
+        assert (codec.decompress(s).pixels == px).all()
+
+
+def test_module_level_functions_mirror_reference_api():
+    import llcomp_b200
+    px = oracle.generate(40, 30, 3, 4, 2)
+    s = llcomp_b200.compressImage(px.reshape(-1), 40, 30, 3)
+    assert s == oracle.compress(px)
+    pixels, width, height, channels = llcomp_b200.decompressImage(s)   # structured binding, llcompd.cpp:26
+    assert (width, height, channels) == (40, 30, 3) and (pixels == px).all()
+    assert llcomp_b200.ext == ".llcomp" and llcomp_b200.magic_revision == 0x79
+
+
+# ---- front end (K1) -----------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,c,tw,th,amp", [
+    (64, 48, 3, 0, 0, 8), (65, 33, 3, 16, 16, 4), (37, 29, 1, 0, 0, 16), (37, 29, 2, 8, 32, 2),
+    (50, 40, 4, 32, 8, 128), (19, 23, 5, 7, 5, 6), (1, 1, 3, 0, 0, 0), (1, 9, 3, 0, 0, 9), (9, 1, 3, 4, 1, 9),
+    (2, 2, 3, 1, 1, 50), (300, 70, 3, 128, 64, 5)])
+def test_frontend_records_equal_oracle(codec, w, h, c, tw, th, amp):
+    import torch
+    rng = np.random.default_rng(w * 1000 + h)
+    n_img = 2
+    imgs = np.stack([rand_image(rng, w, h, c, amp) for _ in range(n_img)])
+    g = codec.geometry(w, h, c, tw, th, n_img)
+    sym = codec.frontend_device(torch.from_numpy(imgs).cuda(), g)
+    codec.finish()
+    got = sym.cpu().numpy().view(np.uint32)
+    want = []
+    for k in range(n_img):
+        for (x0, y0, sw, sh) in tiles_of(w, h, tw or w, th or h):
+            want.append(oracle.frontend(imgs[k], x0, y0, sw, sh))
+    want = np.concatenate(want)
+    assert got.shape == want.shape
+    assert (got == want).all()
+
+
+# ---- whole streams ------------------------------------------------------------------------------
+def test_cfg1_512_rgb_byte_identical(codec, golden_streams):
+    g = next(x for x in golden_streams["whole"] if (x["w"], x["h"], x["c"], x["n"]) == (512, 512, 3, 4))
+    img = oracle.generate(512, 512, 3, 4, 1234)
+    s = codec.compress(img, 512, 512, 3)
+    assert len(s) == g["bytes"] == 402823
+    assert f"{oracle.fnv1a64(s):016x}" == g["fnv1a64"]      # hash of the unmodified reference's stream
+    assert s == oracle.compress(img)
+    assert (codec.decompress(s).pixels == img).all()
+
+
+@pytest.mark.parametrize("w,h,c,n", [(1024, 1024, 3, 0), (1024, 1024, 3, 4), (1024, 1024, 3, 32), (1024, 1024, 4, 8),
+                                     (256, 256, 1, 4), (256, 256, 2, 4), (300, 200, 3, 6), (64, 64, 5, 3)])
+def test_golden_streams(codec, golden_streams, w, h, c, n):
+    g = next(x for x in golden_streams["whole"] if (x["w"], x["h"], x["c"], x["n"]) == (w, h, c, n))
+    img = oracle.generate(w, h, c, n, 1234)
+    s = codec.compress(img, w, h, c)
+    assert len(s) == g["bytes"] and f"{oracle.fnv1a64(s):016x}" == g["fnv1a64"]
+    assert (codec.decompress(s).pixels == img).all()
+
+
+@pytest.mark.parametrize("c", [1, 3])
+def test_uniform_noise_stream_longer_than_raw(codec, c):
+    # the reference overflows here (llcomp.hpp:362); the oracle restatement defines the answer
+    img = oracle.generate(256, 256, c, -1, 1234)
+    s = codec.compress(img, 256, 256, c)
+    assert len(s) > img.size
+    assert s == oracle.compress(img)
+    assert (codec.decompress(s).pixels == img).all()
+
+
+def test_constant_image_carry_runs(codec):
+    for v in (0, 77, 128, 255):
+        img = np.full((96, 80, 3), v, np.uint8)
+        s = codec.compress(img, 80, 96, 3)
+        assert s == oracle.compress(img)
+        assert (codec.decompress(s).pixels == img).all()
+
+
+def test_differential_random(codec):
+    rng = np.random.default_rng(11)
+    for k in range(60):
+        w, h = int(rng.integers(1, 97)), int(rng.integers(1, 97))
+        c = int(rng.choice([1, 2, 3, 3, 3, 4, 6]))
+        amp = int(rng.choice([0, 1, 2, 4, 16, 64, 128]))
+        img = rand_image(rng, w, h, c, amp)
+        s = codec.compress(img, w, h, c)
+        assert s == oracle.compress(img), (w, h, c, amp)
+        assert (codec.decompress(s).pixels == img).all(), (w, h, c, amp)
+
+
+# ---- slices ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,c,n,tw,th", [(1024, 1024, 3, 4, 512, 512), (600, 500, 3, 4, 256, 128),
+                                           (512, 512, 1, -1, 128, 128), (1024, 1024, 3, 4, 1024, 64)])
+def test_slice_payloads_equal_reference_on_tile(codec, golden_streams, w, h, c, n, tw, th):
+    g = next(t for t in golden_streams["tiled"] if (t["w"], t["h"], t["c"], t["n"], t["tile_w"], t["tile_h"]) ==
+             (w, h, c, n, tw, th))
+    img = oracle.generate(w, h, c, n, 1234)
+    s = codec.compress(img, w, h, c, tw, th)
+    W, H, Cc, TW, TH, payloads = split_container(s)
+    assert (W, H, Cc, TW, TH) == (w, h, c, tw, th) and len(payloads) == len(g["tiles"])
+    assert sum(map(len, payloads)) == g["payload_bytes"]
+    for p, t in zip(payloads, g["tiles"]):
+        assert len(p) == t["bytes"] and f"{oracle.fnv1a64(p):016x}" == t["fnv1a64"]
+    assert (codec.decompress(s).pixels == img).all()
+    assert codec.peek(s) == (w, h, c, tw, th)
+
+
+def test_ragged_tiles_random(codec):
+    rng = np.random.default_rng(5)
+    for k in range(12):
+        w, h = int(rng.integers(8, 200)), int(rng.integers(8, 200))
+        c = int(rng.choice([1, 3, 4]))
+        tw, th = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+        img = rand_image(rng, w, h, c, int(rng.choice([0, 3, 40])))
+        s = codec.compress(img, w, h, c, tw, th)
+        _, _, _, _, _, payloads = split_container(s)
+        for p, (x0, y0, sw, sh) in zip(payloads, tiles_of(w, h, tw, th)):
+            assert p == oracle.encode_tile(img, x0, y0, sw, sh), (w, h, c, tw, th, x0, y0)
+        assert (codec.decompress(s).pixels == img).all()
+
+
+def test_single_slice_grid_is_reference_stream(codec):
+    img = oracle.generate(128, 96, 3, 4, 3)
+    assert codec.compress(img, 128, 96, 3, 128, 96) == oracle.compress(img)
+    assert codec.compress(img, 128, 96, 3, 4096, 4096) == oracle.compress(img)
+
+
+# ---- decoder edge behaviour ---------------------------------------------------------------------
+def test_decode_of_reference_encoder_output(codec):
+    for (w, h, c, n) in [(200, 150, 3, 8), (64, 64, 4, 2), (90, 70, 1, 16)]:
+        img = oracle.generate(w, h, c, n, 77)
+        assert (codec.decompress(oracle.compress(img)).pixels == img).all()
+
+
+def test_truncated_and_padded_streams_match_oracle(codec):
+    img = oracle.generate(48, 40, 3, 8, 21)
+    s = oracle.compress(img)
+    assert (codec.decompress(s + bytes(16)).pixels == img).all()          # explicit zeros == zero fill
+    for cut in (1, 2, 5, 40, len(s) - 7):
+        t = s[:len(s) - cut]
+        assert (codec.decompress(t).pixels == oracle.decompress(t)).all(), cut   # same garbage, llcomp.hpp:476-477
+    t = s + b"\xff" * 4
+    assert (codec.decompress(t).pixels == oracle.decompress(t)).all()
+
+
+def test_error_behaviour(codec):
+    from llcomp_b200 import LlcompError
+    with pytest.raises(LlcompError, match="Invalid magic number") as e:      # llcomp.hpp:466
+        codec.decompress(bytes([0x77, 3, 4, 0, 4, 0, 1, 2, 3]))
+    assert e.value.code == 1
+    # a nonzero flag followed by all ones: the exponent runs away -> "Invalid exponent" (llcomp.hpp:233)
+    bad = bytes([0x79, 1, 4, 0, 4, 0, 2, 250]) + b"\xff" * 40
+    with pytest.raises(oracle.OracleError) as eo:
+        oracle.decompress(bad)
+    assert eo.value.code == 2
+    with pytest.raises(LlcompError, match="Invalid exponent") as e:
+        codec.decompress(bad)
+    assert e.value.code == 2
+    with pytest.raises(ValueError):
+        codec.compress(np.zeros(10, np.uint8), 2, 2, 3)                       # assert at llcomp.hpp:361
+
+
+# ---- batches and device-resident buffers ----------------------------------------------------------
+def test_batch_streams_are_standalone_reference_streams(codec):
+    imgs = np.stack([oracle.generate(160, 120, 3, 4, 1234 + k) for k in range(9)])
+    buf, off = codec.compress_batch(imgs)
+    for k in range(9):
+        assert buf[int(off[k]):int(off[k + 1])].tobytes() == oracle.compress(imgs[k])
+    assert (codec.decompress_batch(buf, off) == imgs).all()
+    buf2, off2 = codec.compress_batch(imgs, 64, 64)
+    assert (codec.decompress_batch(buf2, off2) == imgs).all()
+    assert int(off2[-1]) > int(off[-1])
+
+
+def test_device_resident_round_trip(codec):
+    import torch
+    imgs = np.stack([oracle.generate(256, 192, 3, 6, 50 + k) for k in range(5)])
+    g = codec.geometry(256, 192, 3, 128, 64, 5)
+    d_px = torch.from_numpy(imgs).cuda()
+    payload, offsets = codec.encode_device(d_px, g)
+    codec.finish()
+    off = offsets.cpu().numpy()
+    pay = payload.cpu().numpy()
+    k = 0
+    for i in range(5):
+        for (x0, y0, sw, sh) in tiles_of(256, 192, 128, 64):
+            assert pay[off[k]:off[k + 1]].tobytes() == oracle.encode_tile(imgs[i], x0, y0, sw, sh)
+            k += 1
+    out = codec.decode_device(payload, offsets, g)
+    codec.finish()
+    assert (out.cpu().numpy().reshape(imgs.shape) == imgs).all()
+
+
+# ---- BASELINE sizes: size-independent properties + sampled oracle checks ---------------------------
+def test_cfg2_4096_rgb_64_slices(codec):
+    import torch
+    img = oracle.generate(4096, 4096, 3, 4, 1234)
+    g = codec.geometry(4096, 4096, 3, 512, 512, 1)
+    d_px = torch.from_numpy(img).cuda()
+    payload, offsets = codec.encode_device(d_px, g)
+    codec.finish()
+    off = offsets.cpu().numpy()
+    assert off.size == 65 and (np.diff(off) > 0).all()
+    pay = payload[: int(off[-1])].cpu().numpy()
+    tiles = tiles_of(4096, 4096, 512, 512)
+    for k in (0, 7, 27, 36, 56, 63):                                   # corners + interior, vs the oracle
+        x0, y0, sw, sh = tiles[k]
+        assert pay[off[k]:off[k + 1]].tobytes() == oracle.encode_tile(img, x0, y0, sw, sh), k
+    out = codec.decode_device(payload, offsets, g)
+    codec.finish()
+    assert torch.equal(out.view(4096, 4096, 3), d_px)                   # exact round trip of every pixel
+    bpp = 8.0 * int(off[-1]) / (4096 * 4096)
+    assert 11.9 < bpp < 12.6                                           # single slice: 11.994
+
+
+def test_cfg3_gray_noise_round_trip(codec):
+    import torch
+    img = oracle.generate(2048, 2048, 1, -1, 1234)                       # content of config 3 at 1/16 area
+    g = codec.geometry(2048, 2048, 1, 512, 512, 1)
+    d_px = torch.from_numpy(img).cuda()
+    payload, offsets = codec.encode_device(d_px, g)
+    codec.finish()
+    off = offsets.cpu().numpy()
+    assert int(off[-1]) > img.size                                      # ~1.23x raw
+    k = 5
+    x0, y0, sw, sh = tiles_of(2048, 2048, 512, 512)[k]
+    assert payload[int(off[k]):int(off[k + 1])].cpu().numpy().tobytes() == oracle.encode_tile(img, x0, y0, sw, sh)
+    out = codec.decode_device(payload, offsets, g)
+    codec.finish()
+    assert torch.equal(out.view(2048, 2048, 1), d_px)
+
+
+def test_wide_tile_uses_global_row_scratch(codec):
+    # a 20000-wide strip does not fit the shared-memory row buffers of the decoder
+    img = oracle.generate(20000, 6, 3, 4, 8)
+    s = codec.compress(img, 20000, 6, 3)
+    assert s == oracle.compress(img)
+    assert (codec.decompress(s).pixels == img).all()
