@@ -1,0 +1,114 @@
+// llcomp.hpp -- host-side mirror of the reference interface on top of the C ABI.
+//
+// Same namespace, names, signatures, ownership and exceptions as /root/reference/llcomp.hpp:
+//   std::vector<uint8_t> llcomp::compressImage(const std::vector<uint8_t>& rgb, int width, int height, int channels)  (:358)
+//   llcomp::RawImage     llcomp::decompressImage(const std::vector<uint8_t>& data)                                   (:461)
+//   struct RawImage { pixels, width, height, channels }  in this member order (:454-459; llcompd.cpp:26 binds it)
+//   constants ext / revision / magic_revision (:18-20)
+// so llcompc.cpp:33 and llcompd.cpp:26 compile against it unchanged.  All arithmetic happens in
+// libllcomp_b200.so (CUDA, sm_100a); nothing here computes a single sample and there is no CPU fallback.
+//
+// New (the reference has no slicing / batching): Options{tile_w, tile_h, device} overloads and
+// compressBatch / decompressBatch.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/llcomp_b200.h"
+
+namespace llcomp {
+
+constexpr inline auto ext = ".llcomp";                       // llcomp.hpp:18
+constexpr inline uint8_t revision = 2;                       // llcomp.hpp:19
+constexpr inline uint8_t magic_revision = 0x77 + revision;   // llcomp.hpp:20
+
+struct RawImage {                                            // llcomp.hpp:454-459
+    std::vector<uint8_t> pixels;
+    uint16_t width;
+    uint16_t height;
+    uint8_t channels;
+};
+
+struct Options {
+    int tile_w = 0, tile_h = 0;   // 0 = one slice per image: byte-identical to the reference stream
+    int device = 0;
+};
+
+namespace detail {
+struct CtxDeleter { void operator()(llcomp_ctx* c) const { llcomp_b200_ctx_destroy(c); } };
+
+inline llcomp_ctx* context(int device) {
+    static std::mutex mu;
+    static std::vector<std::unique_ptr<llcomp_ctx, CtxDeleter>> ctxs;
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0) throw std::invalid_argument("llcomp: negative device index");
+    if ((size_t)device >= ctxs.size()) ctxs.resize(device + 1);
+    if (!ctxs[device]) {
+        llcomp_ctx* c = nullptr;
+        if (llcomp_b200_ctx_create(device, &c) != LLCOMP_OK)
+            throw std::runtime_error("llcomp: no usable CUDA device (this build has no CPU path)");
+        ctxs[device].reset(c);
+    }
+    return ctxs[device].get();
+}
+
+// The two reference exceptions keep their exact text (llcomp.hpp:233, :466) so callers that print
+// e.what() (llcompd.cpp:33) behave the same.
+[[noreturn]] inline void raise(llcomp_ctx* c, int status) {
+    std::string msg = llcomp_b200_status_string(status);
+    if (status == LLCOMP_ERR_CUDA) msg += std::string(": ") + llcomp_b200_last_error(c);
+    throw std::runtime_error(msg);
+}
+}  // namespace detail
+
+inline std::vector<uint8_t> compressImage(const std::vector<uint8_t>& rgb, int width, int height, int channels,
+                                          const Options& opt) {
+    if (rgb.size() != (size_t)width * height * channels)     // assert at llcomp.hpp:361
+        throw std::invalid_argument("llcomp: rgb.size() != width*height*channels");
+    llcomp_ctx* c = detail::context(opt.device);
+    uint8_t* s = nullptr;
+    size_t n = 0;
+    const int rc = llcomp_b200_encode(c, rgb.data(), width, height, channels, opt.tile_w, opt.tile_h, &s, &n);
+    if (rc != LLCOMP_OK) detail::raise(c, rc);
+    std::vector<uint8_t> out(s, s + n);
+    llcomp_b200_free(s);
+    return out;
+}
+
+inline std::vector<uint8_t> compressImage(const std::vector<uint8_t>& rgb, int width, int height, int channels) {
+    return compressImage(rgb, width, height, channels, Options{});
+}
+
+inline RawImage decompressImage(const std::vector<uint8_t>& data, const Options& opt) {
+    llcomp_ctx* c = detail::context(opt.device);
+    uint8_t* px = nullptr;
+    int w = 0, h = 0, ch = 0;
+    const int rc = llcomp_b200_decode(c, data.data(), data.size(), &px, &w, &h, &ch);
+    if (rc != LLCOMP_OK) detail::raise(c, rc);
+    RawImage img{std::vector<uint8_t>(px, px + (size_t)w * h * ch), (uint16_t)w, (uint16_t)h, (uint8_t)ch};
+    llcomp_b200_free(px);
+    return img;
+}
+
+inline RawImage decompressImage(const std::vector<uint8_t>& data) { return decompressImage(data, Options{}); }
+
+// n equally sized images, pixels back to back -> one complete stream per image.
+inline std::vector<std::vector<uint8_t>> compressBatch(const std::vector<uint8_t>& pixels, int n_images, int width,
+                                                       int height, int channels, const Options& opt = Options{}) {
+    llcomp_geometry g{width, height, channels, opt.tile_w, opt.tile_h, n_images};
+    if (pixels.size() != llcomp_b200_sample_count(&g)) throw std::invalid_argument("llcomp: batch size mismatch");
+    llcomp_ctx* c = detail::context(opt.device);
+    std::vector<uint8_t> buf(llcomp_b200_stream_bound(&g));
+    std::vector<uint64_t> off(n_images + 1);
+    const int rc = llcomp_b200_encode_batch(c, pixels.data(), &g, buf.data(), buf.size(), off.data());
+    if (rc != LLCOMP_OK) detail::raise(c, rc);
+    std::vector<std::vector<uint8_t>> out(n_images);
+    for (int k = 0; k < n_images; ++k) out[k].assign(buf.begin() + off[k], buf.begin() + off[k + 1]);
+    return out;
+}
+
+}  // namespace llcomp

@@ -1,0 +1,69 @@
+"""llcompc / llcompd (C++ host over the C ABI) keep the reference tools' contract (llcompc.cpp, llcompd.cpp):
+one positional argument, `<image>.llcomp` next to the input, exit codes 0/1, reference error text."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(ROOT, "llcomp_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def tools():
+    from llcomp_b200.build import build
+    build()
+    return os.path.join(HOST, "llcompc"), os.path.join(HOST, "llcompd")
+
+
+def write_pnm(path, img):
+    h, w, c = img.shape
+    with open(path, "wb") as f:
+        if c in (1, 3):
+            f.write(b"%s\n%d %d\n255\n" % (b"P5" if c == 1 else b"P6", w, h))
+        else:
+            f.write(b"P7\nWIDTH %d\nHEIGHT %d\nDEPTH %d\nMAXVAL 255\nTUPLTYPE RGB_ALPHA\nENDHDR\n" % (w, h, c))
+        f.write(img.tobytes())
+
+
+def read_pnm_payload(path, n):
+    with open(path, "rb") as f:
+        return np.frombuffer(f.read()[-n:], np.uint8)
+
+
+@pytest.mark.parametrize("c,ext", [(3, ".ppm"), (1, ".pgm"), (4, ".pam")])
+def test_round_trip_through_the_tools(tools, tmp_path, c, ext):
+    llcompc, llcompd = tools
+    img = oracle.generate(200, 120, c, 4, 99)
+    src = str(tmp_path / ("in" + ext))
+    write_pnm(src, img)
+    assert subprocess.run([llcompc, src]).returncode == 0
+    with open(src + ".llcomp", "rb") as f:
+        stream = f.read()
+    assert stream == oracle.compress(img)                       # byte-identical to the reference format
+    assert subprocess.run([llcompd, src + ".llcomp"]).returncode == 0
+    assert (read_pnm_payload(src + ".llcomp" + ext, img.size) == img.reshape(-1)).all()
+
+
+def test_tile_option_and_errors(tools, tmp_path):
+    llcompc, llcompd = tools
+    img = oracle.generate(300, 200, 3, 4, 5)
+    src = str(tmp_path / "t.ppm")
+    write_pnm(src, img)
+    assert subprocess.run([llcompc, src, "--tile", "128x64"]).returncode == 0
+    with open(src + ".llcomp", "rb") as f:
+        assert f.read(1) == b"\xb2"
+    assert subprocess.run([llcompd, src + ".llcomp"]).returncode == 0
+    assert (read_pnm_payload(src + ".llcomp.ppm", img.size) == img.reshape(-1)).all()
+    # reference behaviour: usage / missing file / bad magic all exit 1 (llcompc.cpp:19-29, llcompd.cpp:12-20, :32-35)
+    assert subprocess.run([llcompc], capture_output=True).returncode == 1
+    assert subprocess.run([llcompc, str(tmp_path / "nope.ppm")], capture_output=True).returncode == 1
+    bad = str(tmp_path / "bad.llcomp")
+    with open(bad, "wb") as f:
+        f.write(bytes([0x77, 3, 1, 0, 1, 0, 0]))
+    r = subprocess.run([llcompd, bad], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error decompressing image: Invalid magic number" in r.stderr
