@@ -113,10 +113,15 @@ int llcomp_b200_frontend_device(llcomp_ctx *ctx, const uint8_t *d_pixels, const 
 uint64_t llcomp_b200_launch_count(const llcomp_ctx *ctx);
 /* Device time of the kernels of the LAST encode_device / decode_device call, in milliseconds, measured
  * with CUDA events on the caller's stream when profiling was switched on; names in llcomp_b200_stage_name. */
-#define LLCOMP_B200_N_STAGES 5
+#define LLCOMP_B200_N_STAGES 6
 void llcomp_b200_set_profiling(llcomp_ctx *ctx, int on);
 int llcomp_b200_stage_times(llcomp_ctx *ctx, float *ms_out /* LLCOMP_B200_N_STAGES */);
 const char *llcomp_b200_stage_name(int stage);
+/* Binary decisions coded by the last encode call on this context (bins/s reporting). */
+uint64_t llcomp_b200_last_bin_count(const llcomp_ctx *ctx);
+/* Bytes of HBM the encoder's bin queue (model pass -> range pass) may take; default 40 % of the device.
+ * The slices of one call are coded in as few launch groups as fit.  Tests shrink it to force several groups. */
+void llcomp_b200_set_queue_budget(llcomp_ctx *ctx, uint64_t bytes);
 /* Model table entry of state s: P(bit=1)*256 | next_if_mps<<8 | next_if_lps<<16 (llcomp.hpp:252-281). */
 uint32_t llcomp_b200_debug_table(int s);
 

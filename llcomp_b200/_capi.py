@@ -8,7 +8,7 @@ import os
 from .build import LIB
 
 OK, ERR_BAD_MAGIC, ERR_BAD_EXPONENT, ERR_BAD_ARG, ERR_NOMEM, ERR_OVERFLOW, ERR_CUDA, ERR_TRUNCATED = range(8)
-N_STAGES = 5
+N_STAGES = 6
 
 
 class Geometry(C.Structure):
@@ -52,6 +52,8 @@ SIGNATURES = {
     "llcomp_b200_stage_times": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "llcomp_b200_stage_name": (C.c_char_p, [C.c_int]),
     "llcomp_b200_debug_table": (C.c_uint32, [C.c_int]),
+    "llcomp_b200_set_queue_budget": (None, [_vp, C.c_uint64]),
+    "llcomp_b200_last_bin_count": (C.c_uint64, [_vp]),
 }
 
 _lib = None

@@ -210,6 +210,13 @@ class Codec:
     def set_profiling(self, on: bool):
         self._L.llcomp_b200_set_profiling(self._h, int(on))
 
+    def last_bin_count(self) -> int:
+        return int(self._L.llcomp_b200_last_bin_count(self._h))
+
+    def set_queue_budget(self, nbytes: int):
+        """HBM the encoder's bin queue may take (default 40 % of the device); smaller forces more launch groups."""
+        self._L.llcomp_b200_set_queue_budget(self._h, int(nbytes))
+
     def stage_times(self) -> dict:
         ms = (C.c_float * _capi.N_STAGES)()
         self._check(self._L.llcomp_b200_stage_times(self._h, ms))

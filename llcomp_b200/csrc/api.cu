@@ -2,6 +2,7 @@
 // host-buffer and device-resident entry points.  Replaces the call sites llcompc.cpp:33
 // (compressImage) and llcompd.cpp:26 (decompressImage) of the reference; header layout follows
 // llcomp.hpp:375-378 / :463-470.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,8 +18,24 @@ using namespace llc;
 
 namespace {
 
-enum Stage { kStFrontend = 0, kStCoder, kStScan, kStCompact, kStDecoder };
-const char* const kStageNames[LLCOMP_B200_N_STAGES] = {"frontend", "slice_coder", "scan", "compact", "slice_decoder"};
+enum Stage { kStFrontend = 0, kStModel, kStRange, kStScan, kStCompact, kStDecoder };
+const char* const kStageNames[LLCOMP_B200_N_STAGES] = {"frontend", "model_pass", "range_pass", "scan", "compact",
+                                                       "slice_decoder"};
+
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
 
 template <typename T>
 struct DevBuf {
@@ -40,8 +57,15 @@ struct DevBuf {
 struct llcomp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;          // used by the host-buffer entry points
-    DevBuf<uint32_t> sym;                   // K1 -> K2 records
-    DevBuf<uint8_t> scratch;                // K2 per-slice payloads before compaction
+    DevBuf<uint32_t> sym;                   // K1 -> K2a records
+    DevBuf<unsigned long long> slice_bins;  // K1: exact number of binary decisions per slice
+    DevBuf<uint64_t> qoff;                  // first bin-queue entry of every slice (within its launch group)
+    DevBuf<uint16_t> queue;                 // K2a -> K2b bin queue
+    PinnedBuf<unsigned long long> h_bins;
+    PinnedBuf<uint64_t> h_qoff;
+    uint64_t last_bins = 0;                 // decisions coded by the last encode call
+    uint64_t queue_budget = 0;              // bytes the bin queue may take; slices are processed in groups that fit
+    DevBuf<uint8_t> scratch;                // K2b per-slice payloads before compaction
     DevBuf<uint32_t> slice_bytes;
     DevBuf<int16_t> lines;                  // K5 row scratch when a tile row does not fit in smem
     DevBuf<uint8_t> pixels, payload;        // staging of the host-buffer entry points
@@ -50,9 +74,10 @@ struct llcomp_ctx {
     std::string last_error;
     uint64_t launches = 0;
     bool profiling = false;
-    cudaEvent_t ev[LLCOMP_B200_N_STAGES + 1] = {};
-    bool ev_made = false;
-    int ev_first = -1, ev_last = -1;        // stages recorded by the last device call
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;                // one per kernel launch of the last device call (profiling only)
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
 };
 
 namespace {
@@ -137,22 +162,28 @@ int parse_header(const uint8_t* s, size_t n, llcomp_geometry* g, size_t* hdr, st
     return LLCOMP_OK;
 }
 
-void begin_stages(llcomp_ctx* ctx, cudaStream_t st, int first) {
-    ctx->ev_first = ctx->ev_last = -1;
-    if (!ctx->profiling) return;
-    if (!ctx->ev_made) {
-        for (auto& e : ctx->ev) cudaEventCreate(&e);
-        ctx->ev_made = true;
+cudaEvent_t take_event(llcomp_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
     }
-    cudaEventRecord(ctx->ev[first], st);
-    ctx->ev_first = first;
+    return ctx->ev_pool[ctx->ev_used++];
 }
-void end_stage(llcomp_ctx* ctx, cudaStream_t st, int stage) {
-    ctx->launches++;
-    if (!ctx->profiling) return;
-    cudaEventRecord(ctx->ev[stage + 1], st);
-    ctx->ev_last = stage;
-}
+void begin_call(llcomp_ctx* ctx) { ctx->spans.clear(); ctx->ev_used = 0; }
+// Brackets one kernel launch with events on the launching stream (profiling only) and counts it.
+struct StageScope {
+    llcomp_ctx* ctx; cudaStream_t st; cudaEvent_t b = nullptr;
+    StageScope(llcomp_ctx* c, cudaStream_t s, int stage) : ctx(c), st(s) {
+        ctx->launches++;
+        if (!ctx->profiling) return;
+        cudaEvent_t a = take_event(ctx);
+        b = take_event(ctx);
+        cudaEventRecord(a, st);
+        ctx->spans.push_back({stage, a, b});
+    }
+    ~StageScope() { if (b) cudaEventRecord(b, st); }
+};
 
 }  // namespace
 
@@ -192,6 +223,11 @@ int llcomp_b200_ctx_create(int device, llcomp_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int));
+    if (e == cudaSuccess) {
+        size_t free_b = 0, total_b = 0;
+        e = cudaMemGetInfo(&free_b, &total_b);
+        ctx->queue_budget = (uint64_t)total_b * 2 / 5;       // 40 % of HBM (72 GB on B200)
+    }
     if (e == cudaSuccess) e = configure_slice_coder();
     if (e == cudaSuccess) e = configure_slice_decoder();
     if (e != cudaSuccess) {
@@ -208,8 +244,9 @@ void llcomp_b200_ctx_destroy(llcomp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->sym.release(); ctx->scratch.release(); ctx->slice_bytes.release(); ctx->lines.release();
     ctx->pixels.release(); ctx->payload.release(); ctx->offsets.release();
+    ctx->slice_bins.release(); ctx->qoff.release(); ctx->queue.release(); ctx->h_bins.release(); ctx->h_qoff.release();
     if (ctx->d_status) cudaFree(ctx->d_status);
-    if (ctx->ev_made) for (auto& e : ctx->ev) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -228,11 +265,17 @@ void llcomp_b200_set_profiling(llcomp_ctx* ctx, int on) { if (ctx) ctx->profilin
 int llcomp_b200_stage_times(llcomp_ctx* ctx, float* ms) {
     if (!ctx || !ms) return LLCOMP_ERR_BAD_ARG;
     for (int i = 0; i < LLCOMP_B200_N_STAGES; ++i) ms[i] = 0.f;
-    if (!ctx->profiling || ctx->ev_first < 0) return LLCOMP_OK;
-    CK(cudaEventSynchronize(ctx->ev[ctx->ev_last + 1]));
-    for (int i = ctx->ev_first; i <= ctx->ev_last; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    for (const auto& sp : ctx->spans) {
+        float t = 0.f;
+        CK(cudaEventSynchronize(sp.b));
+        CK(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.stage] += t;
+    }
     return LLCOMP_OK;
 }
+
+uint64_t llcomp_b200_last_bin_count(const llcomp_ctx* ctx) { return ctx ? ctx->last_bins : 0; }
+void llcomp_b200_set_queue_budget(llcomp_ctx* ctx, uint64_t bytes) { if (ctx && bytes) ctx->queue_budget = bytes; }
 
 // ---- device-resident path --------------------------------------------------------------------
 int llcomp_b200_frontend_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const llcomp_geometry* gi, uint32_t* d_sym,
@@ -241,9 +284,11 @@ int llcomp_b200_frontend_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const 
     if (!ctx || !d_pixels || !d_sym || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    begin_stages(ctx, st, kStFrontend);
-    CK(launch_frontend(d_pixels, g, d_sym, st));
-    end_stage(ctx, st, kStFrontend);
+    begin_call(ctx);
+    {
+        StageScope sc(ctx, st, kStFrontend);
+        CK(launch_frontend(d_pixels, g, d_sym, nullptr, st));
+    }
     return LLCOMP_OK;
 }
 
@@ -253,19 +298,64 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
     if (!ctx || !d_pixels || !d_payload || !d_offsets || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const uint64_t ns = g.n_slices();
     CK(ctx->sym.reserve(g.n_samples()));
     CK(ctx->scratch.reserve(payload_capacity(g) + 64));
-    CK(ctx->slice_bytes.reserve(g.n_slices()));
+    CK(ctx->slice_bytes.reserve(ns));
+    CK(ctx->slice_bins.reserve(ns));
+    CK(ctx->qoff.reserve(ns));
+    CK(ctx->h_bins.reserve(ns));
+    CK(ctx->h_qoff.reserve(ns));
+    begin_call(ctx);
 
-    begin_stages(ctx, st, kStFrontend);
-    CK(launch_frontend(d_pixels, g, ctx->sym.p, st));
-    end_stage(ctx, st, kStFrontend);
-    CK(launch_slice_coder(ctx->sym.p, g, ctx->scratch.p, ctx->slice_bytes.p, ctx->d_status, st));
-    end_stage(ctx, st, kStCoder);
-    CK(launch_scan(ctx->slice_bytes.p, g.n_slices(), d_offsets, capacity, ctx->d_status, st));
-    end_stage(ctx, st, kStScan);
-    CK(launch_compact(ctx->scratch.p, g, d_offsets, d_payload, capacity, st));
-    end_stage(ctx, st, kStCompact);
+    // K1: records + exact decision count of every slice
+    CK(cudaMemsetAsync(ctx->slice_bins.p, 0, ns * sizeof(unsigned long long), st));
+    {
+        StageScope sc(ctx, st, kStFrontend);
+        CK(launch_frontend(d_pixels, g, ctx->sym.p, ctx->slice_bins.p, st));
+    }
+    // The one host round trip of the encoder: the counts size the bin queue and split the slices into
+    // launch groups that fit the queue budget (one group unless the batch is huge or very noisy).
+    CK(cudaMemcpyAsync(ctx->h_bins.p, ctx->slice_bins.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t budget_entries = ctx->queue_budget / 2;
+    struct Group { uint64_t s0, count, entries; };
+    std::vector<Group> groups;
+    uint64_t run = 0, start = 0;
+    ctx->last_bins = 0;
+    for (uint64_t k = 0; k < ns; ++k) {
+        ctx->last_bins += ctx->h_bins.p[k];
+        const uint64_t need = (ctx->h_bins.p[k] + kQueuePad + 7) & ~7ull;
+        if (need > budget_entries) { ctx->last_error = "bin queue budget too small for one slice"; return LLCOMP_ERR_NOMEM; }
+        if (run + need > budget_entries) { groups.push_back({start, k - start, run}); start = k; run = 0; }
+        ctx->h_qoff.p[k] = run;
+        run += need;
+    }
+    groups.push_back({start, ns - start, run});
+    uint64_t max_entries = 0;
+    for (const Group& gr : groups) max_entries = std::max(max_entries, gr.entries);
+    CK(ctx->queue.reserve(max_entries + 64));
+    CK(cudaMemcpyAsync(ctx->qoff.p, ctx->h_qoff.p, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+
+    for (const Group& gr : groups) {
+        {
+            StageScope sc(ctx, st, kStModel);
+            CK(launch_model_pass(ctx->sym.p, g, gr.s0, gr.count, ctx->queue.p, ctx->qoff.p, st));
+        }
+        {
+            StageScope sc(ctx, st, kStRange);
+            CK(launch_range_pass(ctx->queue.p, ctx->qoff.p, ctx->slice_bins.p, g, gr.s0, gr.count, ctx->scratch.p,
+                                 ctx->slice_bytes.p, ctx->d_status, st));
+        }
+    }
+    {
+        StageScope sc(ctx, st, kStScan);
+        CK(launch_scan(ctx->slice_bytes.p, ns, d_offsets, capacity, ctx->d_status, st));
+    }
+    {
+        StageScope sc(ctx, st, kStCompact);
+        CK(launch_compact(ctx->scratch.p, g, d_offsets, d_payload, capacity, st));
+    }
     return LLCOMP_OK;
 }
 
@@ -277,9 +367,11 @@ int llcomp_b200_decode_device(llcomp_ctx* ctx, const uint8_t* d_payload, const u
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const uint64_t lb = decoder_line_scratch_bytes(g);
     if (lb) CK(ctx->lines.reserve(lb / 2));
-    begin_stages(ctx, st, kStDecoder);
-    CK(launch_slice_decoder(d_payload, d_offsets, g, d_pixels, ctx->lines.p, ctx->d_status, st));
-    end_stage(ctx, st, kStDecoder);
+    begin_call(ctx);
+    {
+        StageScope sc(ctx, st, kStDecoder);
+        CK(launch_slice_decoder(d_payload, d_offsets, g, d_pixels, ctx->lines.p, ctx->d_status, st));
+    }
     return LLCOMP_OK;
 }
 

@@ -91,6 +91,9 @@ __host__ __device__ __forceinline__ uint64_t scratch_cap(const Slice& sl) {
     return 2 * sl.n + kScratchSlack;
 }
 
+// Bin queue between the model pass and the range pass: no-op entries appended to every slice.
+constexpr int kQueuePad = 512;
+
 // Device-side status word: first error wins.
 enum : int { kDevOk = 0, kDevOverflow = 5, kDevBadExponent = 2 };
 

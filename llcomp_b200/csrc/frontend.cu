@@ -44,12 +44,14 @@ __device__ __forceinline__ int plane_value(const uint8_t* __restrict__ p, int C,
 // v1 mapping: one thread per pixel, neighbours re-read through L1/L2.
 template <int CT>
 __global__ void __launch_bounds__(256) k_frontend_simple(const uint8_t* __restrict__ pixels, Geom g,
-                                                         uint32_t* __restrict__ sym) {
+                                                         uint32_t* __restrict__ sym,
+                                                         unsigned long long* __restrict__ slice_bins) {
     const int C = CT ? CT : g.C;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xi = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int img = blockIdx.z;
-    if (x >= g.W) return;
+    const bool valid = xi < g.W;
+    const int x = valid ? xi : g.W - 1;          // out-of-range lanes shadow the last pixel and store nothing
 
     const int tx = x / g.tw, ty = y / g.th;
     const int x0 = tx * g.tw, y0 = ty * g.th;
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(256) k_frontend_simple(const uint8_t* __restri
     const uint8_t* p = row0 + (size_t)x * C;
     uint32_t* out = sym + (size_t)img * g.image_samples() + ((size_t)y0 * g.W + (size_t)x0 * sh) * C +
                     ((size_t)h * sw + w) * C;
+    unsigned bins = 0;
 
 #pragma unroll
     for (int i = 0; i < (CT ? CT : C); ++i) {
@@ -77,20 +80,36 @@ __global__ void __launch_bounds__(256) k_frontend_simple(const uint8_t* __restri
                    3025 * quant5(T - t);                       // :424-429 (aliased multipliers are normative)
         int diff = cur - median3(l, l + t - tl, t);            // :430-431
         if (hash < 0) { hash = -hash; diff = -diff; }          // :433-436
-        out[i] = pack_symbol(hash, diff);
+        if (valid) out[i] = pack_symbol(hash, diff);
+        // decisions putSymbol will emit for this residual (llcomp.hpp:183-204): 1, or 2*ilog2|d|+3
+        bins += diff ? 2u * (31 - __clz(abs(diff))) + 3u : 1u;
+    }
+
+    if (slice_bins) {
+        // one counter per slice; a warp that lies inside one tile adds once
+        const unsigned slice = (unsigned)img * g.slices_per_image() + ty * g.tiles_x + tx;
+        const unsigned mine = valid ? bins : 0u;
+        const unsigned first = __shfl_sync(0xFFFFFFFFu, slice, 0);
+        if (__all_sync(0xFFFFFFFFu, slice == first)) {
+            const unsigned sum = __reduce_add_sync(0xFFFFFFFFu, mine);
+            if ((threadIdx.x & 31) == 0 && sum) atomicAdd(slice_bins + slice, (unsigned long long)sum);
+        } else if (mine) {
+            atomicAdd(slice_bins + slice, (unsigned long long)mine);
+        }
     }
 }
 
-cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st) {
+cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, unsigned long long* d_slice_bins,
+                            cudaStream_t st) {
     dim3 block(256);
     dim3 grid((g.W + 255) / 256, g.H, g.n_images);
     if (g.H > 65535 || g.n_images > 65535) return cudaErrorInvalidValue;
     switch (g.C) {
-        case 1: k_frontend_simple<1><<<grid, block, 0, st>>>(d_pixels, g, d_sym); break;
-        case 2: k_frontend_simple<2><<<grid, block, 0, st>>>(d_pixels, g, d_sym); break;
-        case 3: k_frontend_simple<3><<<grid, block, 0, st>>>(d_pixels, g, d_sym); break;
-        case 4: k_frontend_simple<4><<<grid, block, 0, st>>>(d_pixels, g, d_sym); break;
-        default: k_frontend_simple<0><<<grid, block, 0, st>>>(d_pixels, g, d_sym); break;
+        case 1: k_frontend_simple<1><<<grid, block, 0, st>>>(d_pixels, g, d_sym, d_slice_bins); break;
+        case 2: k_frontend_simple<2><<<grid, block, 0, st>>>(d_pixels, g, d_sym, d_slice_bins); break;
+        case 3: k_frontend_simple<3><<<grid, block, 0, st>>>(d_pixels, g, d_sym, d_slice_bins); break;
+        case 4: k_frontend_simple<4><<<grid, block, 0, st>>>(d_pixels, g, d_sym, d_slice_bins); break;
+        default: k_frontend_simple<0><<<grid, block, 0, st>>>(d_pixels, g, d_sym, d_slice_bins); break;
     }
     return cudaGetLastError();
 }

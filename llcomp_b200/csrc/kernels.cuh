@@ -4,12 +4,18 @@
 
 namespace llc {
 
-// K1  pixels -> records (frontend.cu)
-cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st);
+// K1  pixels -> records, plus the exact number of binary decisions of every slice (frontend.cu).
+//     d_slice_bins (n_slices counters) must be zero on entry; nullptr skips the counting.
+cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym,
+                            unsigned long long* d_slice_bins, cudaStream_t st);
 
-// K2  records -> per-slice scratch payloads + byte counts (coder.cu)
-cudaError_t launch_slice_coder(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch,
-                               uint32_t* d_slice_bytes, int* d_status, cudaStream_t st);
+// K2a records -> bin queue (model pass, state in shared memory); K2b bin queue -> per-slice scratch payloads
+//     and byte counts (range pass).  Both work on slices [s0, s0+count); d_qoff[s] = first queue entry of slice s.
+cudaError_t launch_model_pass(const uint32_t* d_sym, const Geom& g, uint64_t s0, uint64_t count, uint16_t* d_queue,
+                              const uint64_t* d_qoff, cudaStream_t st);
+cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, const unsigned long long* d_nbins,
+                              const Geom& g, uint64_t s0, uint64_t count, uint8_t* d_scratch, uint32_t* d_slice_bytes,
+                              int* d_status, cudaStream_t st);
 cudaError_t configure_slice_coder();
 
 // K3  exclusive scan of slice byte counts; K4 compaction into one contiguous payload (pack.cu)

@@ -242,6 +242,25 @@ def test_batch_streams_are_standalone_reference_streams(codec):
     assert int(off2[-1]) > int(off[-1])
 
 
+def test_small_queue_budget_forces_launch_groups(codec):
+    import torch
+    imgs = np.stack([oracle.generate(128, 96, 3, 8, 70 + k) for k in range(7)])
+    g = codec.geometry(128, 96, 3, 64, 48, 7)
+    d_px = torch.from_numpy(imgs).cuda()
+    ref_payload, ref_off = codec.encode_device(d_px, g)
+    codec.finish()
+    codec.set_queue_budget(200_000)                 # ~3 slices per group instead of all 28
+    try:
+        payload, off = codec.encode_device(d_px, g)
+        codec.finish()
+    finally:
+        codec.set_queue_budget(64 << 30)
+    assert torch.equal(off, ref_off)
+    n = int(off[-1])
+    assert torch.equal(payload[:n], ref_payload[:n])
+    assert payload[int(off[4]):int(off[5])].cpu().numpy().tobytes() == oracle.encode_tile(imgs[1], 0, 0, 64, 48)
+
+
 def test_device_resident_round_trip(codec):
     import torch
     imgs = np.stack([oracle.generate(256, 192, 3, 6, 50 + k) for k in range(5)])
