@@ -263,7 +263,7 @@ def main():
     if not args.no_e2e:
         h_px = torch.empty((n_img, H, W, C), dtype=torch.uint8, pin_memory=True)
         h_px.copy_(px)
-        out_cap = raw + 64 * n_img + hdr * n_img
+        out_cap = raw + 384 * n_img + hdr * n_img
         h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
         h_off = torch.zeros(n_img + 1, dtype=torch.int64, pin_memory=True)
         h_back = torch.empty((n_img, H, W, C), dtype=torch.uint8, pin_memory=True)

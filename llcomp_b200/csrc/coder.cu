@@ -24,41 +24,27 @@ __constant__ ModelTables c_tables = make_tables();
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-// Bin-queue entry (u16): bits 0..8 = M, bit 15 = "bit is 0".  With P = P(bit=1)*256 of the context:
-//   bit 1: M = P,       A = 0     range' = (range*M + A) >> 8 = range*P >> 8              (llcomp.hpp:62,69)
-//   bit 0: M = 256 - P, A = 255   range' = range - (range*P >> 8) = ceil(range*(256-P)/256) (llcomp.hpp:66)
-// and low += range - range' exactly when bit is 1 (llcomp.hpp:68).  M = 256, A = 0 is a no-op (padding).
-constexpr uint32_t kNoopEntry = 0x0100u;
+// Bin-queue entry (u16): bits 0..7 = M, bit 15 = "the decision is a 0".  With P = P(bit=1)*256 of the context:
+//   bit 1: M = P,       A = 0     range' = (range*M + A) >> 8 = range*P >> 8                (llcomp.hpp:62,69)
+//   bit 0: M = 256 - P, A = 255   range' = range - (range*P >> 8) = ceil(range*(256-P)/256)   (llcomp.hpp:66)
+// and low += range - range' exactly when the decision is a 1 (llcomp.hpp:68).  P is in [7,247], so M fits a byte.
 // The front end counts the decisions of every slice exactly, so the host lays the queue out without slack
-// beyond kQueuePad no-op entries per slice (whole-block reads of the range pass) and 16-byte alignment.
-
+// beyond kQueuePad entries per slice (16-byte alignment, whole-vector reads of the last partial vector).
 
 // ---------------------------------------------------------------------------------------------------
 // K2a
 // ---------------------------------------------------------------------------------------------------
 constexpr int kModelSmem = kStateBytes + 256 * 4;
 
-// One decision of sub-state `ctx` (compile-time byte of the row half `half`): look the entry up, store it,
-// advance the state (llcomp.hpp:440-443).  tab2[s*2+bit] = entry | next_state << 16.
-template <int kByte>
-__device__ __forceinline__ void model_step(bool active, uint32_t& half, uint32_t bit, const uint32_t* tab2,
-                                           uint16_t* q) {
-    if (active) {
-        const uint32_t s = (half >> (8 * kByte)) & 0xFFu;
-        const uint32_t w = tab2[s * 2 + bit];
-        *q = (uint16_t)w;
-        half = __byte_perm(half, w, kByte == 0 ? 0x3216 : kByte == 1 ? 0x3260 : kByte == 2 ? 0x3610 : 0x6210);
-    }
-}
-
 __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ sym, Geom g, uint64_t s0,
                                                    uint16_t* __restrict__ queue,
                                                    const uint64_t* __restrict__ q_off) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint2* state = reinterpret_cast<uint2*>(smem);                         // one 8-byte row per context
-    uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kStateBytes);
+    uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kStateBytes);     // [state*2 + bit] = entry | next << 16
 
     const int lane = threadIdx.x;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint64_t s = s0 + blockIdx.x;
     const Slice sl = slice_of(g, s);
     const uint32_t* in = sym + sl.sym_off;
@@ -74,7 +60,6 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
     }
     __syncwarp();
 
-    uint64_t qpos = 0;                                                    // entries written so far (warp-uniform)
     uint32_t rec_next = lane < n ? in[lane] : 0u;
     for (uint64_t base = 0; base < n; base += 32) {
         const uint32_t rec = rec_next;
@@ -86,17 +71,17 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
         const uint32_t hash = rec >> 11;
         const int d = ((int)(rec << 21)) >> 21;
         const uint32_t a = (uint32_t)abs(d);
-        const int e = a ? 31 - __clz(a) : 0;
-        const uint32_t nb = valid ? (a ? 2u * e + 3u : 1u) : 0u;
+        const int e = a ? 31 - __clz(a) : -1;                             // -1 marks a zero residual
+        const uint32_t nb = valid ? 2u * e + 3u : 0u;                     // 1 decision for zero, else 2e+3
 
-        uint32_t off = nb;                                                // exclusive scan of the bin counts
+        // exclusive scan of the decision counts (<= 19, five bit planes, no dependent shuffles)
+        uint32_t off = 0, total = 0;
 #pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            const uint32_t y = __shfl_up_sync(kFull, off, dlt);
-            if (lane >= dlt) off += y;
+        for (int b = 0; b < 5; ++b) {
+            const uint32_t m = __ballot_sync(kFull, (nb >> b) & 1u);
+            off += __popc(m & lt_mask) << b;
+            total += __popc(m) << b;
         }
-        const uint32_t total = __shfl_sync(kFull, off, 31);
-        off -= nb;
 
         // lanes with the same context form a chain; its first lane carries the row through the members
         const uint32_t key = valid ? hash : (0x10000u | lane);
@@ -105,6 +90,8 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
         const int rounds = __reduce_max_sync(kFull, valid ? __popc(members) : 0);
         uint2 row = make_uint2(0, 0);
         if (leader) row = state[hash];
+        uint32_t s0b = row.x & 0xFFu, s1b = (row.x >> 8) & 0xFFu, s2b = (row.x >> 16) & 0xFFu, s3b = row.x >> 24;
+        uint32_t s4b = row.y & 0xFFu, s5b = (row.y >> 8) & 0xFFu, s6b = (row.y >> 16) & 0xFFu, s7b = row.y >> 24;
 
         for (int r = 0; r < rounds; ++r) {
             const bool has = leader && members != 0;
@@ -113,80 +100,117 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
             const int md = __shfl_sync(kFull, d, src);
             const uint32_t mo = __shfl_sync(kFull, off, src);
             const uint32_t ma = (uint32_t)abs(md);
-            const int me = ma ? 31 - __clz(ma) : 0;
-            uint16_t* qs = q + qpos + mo;
+            const int me = ma ? 31 - __clz(ma) : -1;
+            const int maxe = __reduce_max_sync(kFull, has ? me : -1);
+            uint16_t* qs = q + mo;
 
-            model_step<0>(has, row.x, ma == 0, tab2, qs);                                 // :187 / :204
-            if (__any_sync(kFull, has && ma)) {
-                model_step<1>(has && ma, row.x, me >= 1, tab2, qs + 1);                   // :190-193, ctx min(1+k,4)
-                model_step<2>(has && me >= 1, row.x, me >= 2, tab2, qs + 2);
-                model_step<3>(has && me >= 2, row.x, me >= 3, tab2, qs + 3);
-                for (int j = 0; __any_sync(kFull, has && me >= 3 && j <= me - 3); ++j)
-                    model_step<0>(has && me >= 3 && j <= me - 3, row.y, j < me - 3, tab2, qs + 4 + j);   // ctx 4
-                model_step<1>(has && me >= 1, row.y, (ma >> max(me - 1, 0)) & 1u, tab2, qs + me + 2);         // ctx 5, :195-198
-                for (int j = 0; __any_sync(kFull, has && me >= 2 && j <= me - 2); ++j)
-                    model_step<2>(has && me >= 2 && j <= me - 2, row.y, (ma >> max(me - 2 - j, 0)) & 1u, tab2,
-                                  qs + me + 3 + j);                                                       // ctx 6
-                model_step<3>(has && ma, row.y, md < 0, tab2, qs + 2 * me + 2);                         // ctx 7, :200-202
+            // the sub-states are independent of one another: issue every look-up of the straight part first
+            const uint32_t w0 = tab2[s0b * 2 + (me < 0)];                                   // ctx 0, :187 / :204
+            const uint32_t w1 = tab2[s1b * 2 + (me >= 1)];                                  // ctx 1..3, :190-193
+            const uint32_t w2 = tab2[s2b * 2 + (me >= 2)];
+            const uint32_t w3 = tab2[s3b * 2 + (me >= 3)];
+            const uint32_t w5 = tab2[s5b * 2 + ((ma >> max(me - 1, 0)) & 1u)];             // ctx 5, first mantissa bit
+            const uint32_t w7 = tab2[s7b * 2 + (md < 0)];                                   // ctx 7, sign, :200-202
+            if (has) { qs[0] = (uint16_t)w0; s0b = w0 >> 16; }
+            if (maxe >= 0) {
+                if (has && me >= 0) {
+                    qs[1] = (uint16_t)w1; s1b = w1 >> 16;
+                    qs[2 * me + 2] = (uint16_t)w7; s7b = w7 >> 16;
+                }
+                if (has && me >= 1) {
+                    qs[2] = (uint16_t)w2; s2b = w2 >> 16;
+                    qs[me + 2] = (uint16_t)w5; s5b = w5 >> 16;
+                }
+                if (has && me >= 2) { qs[3] = (uint16_t)w3; s3b = w3 >> 16; }
+                for (int j = 0; j <= maxe - 3; ++j) {                                       // ctx 4: positions 4..e+1
+                    const uint32_t w4 = tab2[s4b * 2 + (j < me - 3)];
+                    if (has && j <= me - 3) { qs[4 + j] = (uint16_t)w4; s4b = w4 >> 16; }
+                }
+                for (int j = 0; j <= maxe - 2; ++j) {                                       // ctx 6: mantissa bits e-2..0
+                    const uint32_t w6 = tab2[s6b * 2 + ((ma >> max(me - 2 - j, 0)) & 1u)];
+                    if (has && j <= me - 2) { qs[me + 3 + j] = (uint16_t)w6; s6b = w6 >> 16; }
+                }
             }
         }
-        if (leader) state[hash] = row;
+        if (leader)
+            state[hash] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
+                                     s4b | (s5b << 8) | (s6b << 16) | (s7b << 24));
         __syncwarp();
-        qpos += total;
+        q += total;
     }
-
-    // pad with no-ops so the range pass can read whole blocks
-    for (int i = lane; i < kQueuePad; i += 32) q[qpos + i] = (uint16_t)kNoopEntry;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // K2b
 // ---------------------------------------------------------------------------------------------------
-struct RangeEnc {
-    uint32_t low, range;
-    int held;           // outstanding_byte (llcomp.hpp:85), -1 until the first byte is latched
-    uint32_t pending;   // outstanding_count (llcomp.hpp:84)
-    uint8_t* out;
-    uint32_t pos, cap;
-    bool owner;         // one lane of the slice's lane group writes; all of them count
+struct ByteTail {           // byte/carry side of the encoder
+    uint32_t low;
+    uint32_t hp;            // bits 0..7 outstanding_byte (llcomp.hpp:85), bit 8 = nothing latched yet,
+                            // bits 9.. outstanding_count (llcomp.hpp:84); "plain" state <=> hp < 0x100
+    uint8_t* outp;          // where the next byte goes (all lanes of a slice store the same byte there)
+};
+constexpr uint32_t kHpEmpty = 0x100u;
 
-    __device__ __forceinline__ void emit(uint32_t b) {
-        if (owner && pos < cap) out[pos] = (uint8_t)b;
-        ++pos;                                               // keeps counting so overflow is detectable
+// Everything of renorm_encoder's loop body (llcomp.hpp:40-54) that the inlined fast path does not cover:
+// the first latch, deferred 0xFF bytes and their flush.  Rare, so kept out of line to keep the chain's code small.
+__device__ __noinline__ ByteTail renorm_slow(ByteTail t) {
+    uint32_t held = t.hp & 0xFFu, pending = t.hp >> 9;
+    if (t.hp & kHpEmpty) {
+        held = t.low >> 8;                                   // first byte: just latch (low < 0x10000 here)
+    } else if (t.low <= 0xFF00u) {
+        *t.outp++ = (uint8_t)held;
+        for (; pending; --pending) *t.outp++ = 0xFFu;
+        held = t.low >> 8;
+    } else if (t.low >= 0x10000u) {
+        *t.outp++ = (uint8_t)(held + 1);
+        for (; pending; --pending) *t.outp++ = 0x00u;
+        held = (t.low >> 8) & 0xFFu;
+    } else {
+        ++pending;
     }
-    // Byte/carry half of one pass of renorm_encoder's loop body (llcomp.hpp:40-55).
+    t.hp = held | (pending << 9);
+    return t;
+}
+
+// prmt with the selector's "replicate the sign of the selected byte" bit (bit 3 of a nibble), which
+// __byte_perm masks off: turns the flag bit of an entry into A = 0x00 / 0xFF in one instruction.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
+
+struct RangeEnc {
+    ByteTail t;
+    uint32_t range;
+
     __device__ __forceinline__ void shift_low() {
-        if (held < 0) {
-            held = (int)(low >> 8);
-        } else if (low <= 0xFF00u) {
-            emit((uint32_t)held);
-            for (; pending; --pending) emit(0xFFu);
-            held = (int)(low >> 8);
-        } else if (low >= 0x10000u) {
-            emit((uint32_t)held + 1u);
-            for (; pending; --pending) emit(0x00u);
-            held = (int)((low >> 8) & 0xFFu);
+        // plain byte or carry with nothing deferred: emit held (+1 on carry), latch the next byte
+        if (t.hp < kHpEmpty && (t.low - 0xFF01u) >= 0xFFu) {
+            *t.outp++ = (uint8_t)(t.hp + (t.low >> 16));
+            t.hp = (t.low >> 8) & 0xFFu;
         } else {
-            ++pending;
+            t = renorm_slow(t);
         }
-        low = (low & 0xFFu) << 8;
+        t.low = (t.low & 0xFFu) << 8;
     }
-    // One decision, llcomp.hpp:60-73 in the (M, A) form described above.
-    __device__ __forceinline__ void put(uint32_t entry) {
-        const uint32_t m = entry & 0x1FFu;
-        const uint32_t a = (entry & 0x8000u) ? 255u : 0u;
+    // One decision, llcomp.hpp:60-73 in the (M, A) form above; range' >= 1, so one renormalisation step suffices.
+    __device__ __forceinline__ void put(uint32_t m, uint32_t a, bool is_one) {
         const uint32_t x = range * m + a;
         const uint32_t r = x >> 8;
-        if (a == 0) low += range - r;
-        if (x < 0x10000u) {                                  // range' < 0x100: renormalise once (range' >= 1)
+        if (is_one) t.low += range - r;
+        range = r;
+        if (__builtin_expect(r < 0x100u, 0)) {
             shift_low();
-            range = x & 0xFFFFFF00u;                         // == r << 8
-        } else {
-            range = r;
+            range = r << 8;
         }
     }
-    __device__ __forceinline__ void finish() {               // llcomp.hpp:75-81
-        low += 0xFFu; shift_low();                           // range = 0xFF both times: always renormalises
+    __device__ __forceinline__ void put2(uint32_t w) {      // two packed entries
+        put(w & 0xFFu, prmt(w, 0x4449), !(w & 0x8000u));
+        put(prmt(w, 0x4442), prmt(w, 0x444B), (int)w >= 0);
+    }
+    __device__ __forceinline__ void finish() {               // llcomp.hpp:75-81 (range = 0xFF: always renormalises)
+        t.low += 0xFFu; shift_low();
         shift_low();
     }
 };
@@ -198,47 +222,68 @@ __global__ void __launch_bounds__(32) k_range_pass(const uint16_t* __restrict__ 
                                                    uint32_t n_launch, uint8_t* __restrict__ scratch,
                                                    uint32_t* __restrict__ slice_bytes, int* __restrict__ status) {
     constexpr int L = 32 / S;                                // lanes per slice
-    constexpr int kBlock = L * 8;                            // entries per refill of one slice
     __shared__ uint4 stage[2][32];
 
     const int lane = threadIdx.x, grp = lane / L, sub = lane % L;
-    const uint32_t k = blockIdx.x * S + grp;                 // slice index within this launch
-    const bool live = k < n_launch;
-    const uint64_t s = s0 + (live ? k : 0);
+    // slice of this lane group; surplus groups of the last warp shadow the last slice (same bytes, same place)
+    const uint32_t k = min(blockIdx.x * S + grp, n_launch - 1);
+    const uint64_t s = s0 + k;
     const Slice sl = slice_of(g, s);
-    const uint4* src = reinterpret_cast<const uint4*>(queue + q_off[s]) + sub;
-    const uint64_t nb = live ? n_bins[s] : 0;
-    const uint32_t my_blocks = (uint32_t)((nb + kBlock - 1) / kBlock);
+    const uint4* src = reinterpret_cast<const uint4*>(queue + q_off[s]);
+    const uint64_t nb = n_bins[s];
+    uint32_t n_vec = (uint32_t)(nb / 8);                     // whole 8-entry vectors; the rest is the tail
+    uint32_t rest = (uint32_t)(nb % 8);
+    const uint32_t my_blocks = (n_vec + L - 1) / L;
     const uint32_t n_blocks = __reduce_max_sync(kFull, my_blocks);
-    const uint4 noop = make_uint4(kNoopEntry * 0x10001u, kNoopEntry * 0x10001u, kNoopEntry * 0x10001u,
-                                  kNoopEntry * 0x10001u);
 
+    uint8_t* const out0 = scratch + scratch_off(sl, s);
+    uint8_t* const out_end = out0 + scratch_cap(sl);
     RangeEnc enc;
-    enc.low = 0; enc.range = 0xFF00u; enc.held = -1; enc.pending = 0;     // llcomp.hpp:35
-    enc.out = scratch + scratch_off(sl, s);
-    enc.pos = 0; enc.cap = (uint32_t)min(scratch_cap(sl), (uint64_t)0xFFFFFFFFu);
-    enc.owner = live && sub == 0;
+    enc.t.low = 0; enc.range = 0xFF00u; enc.t.hp = kHpEmpty;                    // llcomp.hpp:35
+    enc.t.outp = out0;
+    bool overflow = false;
+    // A slice that outgrows its scratch stops coding (its remaining vectors are skipped), rewinds so that the
+    // few bytes finish() still writes stay inside the scratch, and raises the overflow status.
+    auto guard = [&](uint32_t upcoming) {
+        if (enc.t.outp + (enc.t.hp >> 9) + upcoming + 8 > out_end) {
+            overflow = true; n_vec = 0; rest = 0; enc.t.outp = out0; enc.t.hp = kHpEmpty;
+        }
+    };
 
-    uint4 r0 = 0 < my_blocks ? src[0] : noop;
-    uint4 r1 = 1 < my_blocks ? src[L] : noop;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    uint4 r0 = sub < n_vec ? src[sub] : zero4;
+    uint4 r1 = L + sub < n_vec ? src[L + sub] : zero4;
     for (uint32_t b = 0; b < n_blocks; ++b) {
         stage[b & 1][lane] = r0;
         __syncwarp();
         r0 = r1;
-        r1 = b + 2 < my_blocks ? src[(size_t)(b + 2) * L] : noop;         // two refills ahead of the chain
+        {
+            const uint64_t v = (uint64_t)(b + 2) * L + sub;             // two refills ahead of the chain
+            r1 = v < n_vec ? src[v] : zero4;
+        }
+        guard(L * 8);     // a block emits at most one byte per decision plus the bytes deferred so far
 #pragma unroll 1
         for (int j = 0; j < L; ++j) {
-            const uint4 w = stage[b & 1][grp * L + j];
-            enc.put(w.x & 0xFFFFu); enc.put(w.x >> 16);
-            enc.put(w.y & 0xFFFFu); enc.put(w.y >> 16);
-            enc.put(w.z & 0xFFFFu); enc.put(w.z >> 16);
-            enc.put(w.w & 0xFFFFu); enc.put(w.w >> 16);
+            if (b * L + j < n_vec) {
+                const uint4 w = stage[b & 1][grp * L + j];
+                enc.put2(w.x); enc.put2(w.y); enc.put2(w.z); enc.put2(w.w);
+            }
         }
     }
+    // tail: the nb % 8 entries of the last, partial vector
+    {
+        const uint16_t* tq = reinterpret_cast<const uint16_t*>(src + n_vec);
+        guard(8);
+        for (uint32_t i = 0; i < rest; ++i) {
+            const uint32_t e = tq[i];
+            enc.put(e & 0xFFu, (e & 0x8000u) ? 255u : 0u, !(e & 0x8000u));
+        }
+    }
+    guard(0);
     enc.finish();                                                         // llcomp.hpp:449
-    if (enc.owner) {
-        slice_bytes[s] = enc.pos;
-        if (enc.pos > enc.cap) atomicCAS(status, kDevOk, kDevOverflow);
+    if (sub == 0) {
+        slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(enc.t.outp - out0);
+        if (overflow) atomicCAS(status, kDevOk, kDevOverflow);
     }
 }
 
@@ -258,10 +303,11 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
                               const Geom& g, uint64_t s0, uint64_t count, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                               int* d_status, cudaStream_t st) {
     if (count == 0 || count > 0x3FFFFFFFull) return cudaErrorInvalidValue;
-    // one slice per warp until the warps outnumber ~2 per scheduler (4 x 148 of them), then share warps
+    // one slice per warp while every warp can have a scheduler of its own (4 x 148 of them); beyond that,
+    // slices share warps: the chain is latency-bound, so a second slice in the same warp is nearly free
     const unsigned n = (unsigned)count;
-    if (n <= 1536) k_range_pass<1><<<n, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
-    else if (n <= 3072) k_range_pass<2><<<(n + 1) / 2, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
+    if (n <= 592) k_range_pass<1><<<n, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
+    else if (n <= 1184) k_range_pass<2><<<(n + 1) / 2, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
     else k_range_pass<4><<<(n + 3) / 4, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
     return cudaGetLastError();
 }

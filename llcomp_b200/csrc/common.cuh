@@ -83,7 +83,7 @@ __host__ __device__ __forceinline__ Slice slice_of(const Geom& g, uint64_t s) {
 // Scratch given to slice s by the coder: room for 2x the raw size plus slack (uniform noise codes to
 // ~1.25x raw); a slice that still outgrows it raises LLCOMP_ERR_OVERFLOW instead of the reference's
 // heap overflow (llcomp.hpp:362).
-constexpr uint64_t kScratchSlack = 64;
+constexpr uint64_t kScratchSlack = 384;   // >= one refill block of the range pass (256 decisions) + finish()
 __host__ __device__ __forceinline__ uint64_t scratch_off(const Slice& sl, uint64_t s) {
     return 2 * sl.sym_off + kScratchSlack * s;
 }
@@ -91,8 +91,8 @@ __host__ __device__ __forceinline__ uint64_t scratch_cap(const Slice& sl) {
     return 2 * sl.n + kScratchSlack;
 }
 
-// Bin queue between the model pass and the range pass: no-op entries appended to every slice.
-constexpr int kQueuePad = 512;
+// Bin queue between the model pass and the range pass: slack entries after every slice (alignment, tail vector).
+constexpr int kQueuePad = 64;
 
 // Device-side status word: first error wins.
 enum : int { kDevOk = 0, kDevOverflow = 5, kDevBadExponent = 2 };

@@ -55,7 +55,7 @@ def test_geometry_helpers(L):
     g = Geometry(4096, 4096, 3, 512, 512, 1)
     assert L.llcomp_b200_slice_count(C.byref(g)) == 64
     assert L.llcomp_b200_sample_count(C.byref(g)) == 4096 * 4096 * 3
-    assert L.llcomp_b200_payload_capacity(C.byref(g)) == 2 * 4096 * 4096 * 3 + 64 * 64
+    assert L.llcomp_b200_payload_capacity(C.byref(g)) == 2 * 4096 * 4096 * 3 + 384 * 64
     g = Geometry(1024, 1024, 3, 0, 0, 1024)
     assert L.llcomp_b200_slice_count(C.byref(g)) == 1024
     g = Geometry(600, 500, 3, 256, 128, 2)
