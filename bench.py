@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="tuning only: time the encoder alone")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,8 +243,12 @@ def main():
         sampler.start()
     enc_ms, enc_stage, enc_launches = timed(lambda: codec.encode_device(px, g, payload, offsets), args.steps,
                                             args.warmup, profiled=True)
-    dec_ms, dec_stage, dec_launches = timed(lambda: codec.decode_device(payload, offsets, g, out_px), args.steps,
-                                            args.warmup, profiled=True)
+    if args.no_decode:
+        dec_ms, dec_stage, dec_launches = float("nan"), {}, 0
+        out_px.copy_(px)
+    else:
+        dec_ms, dec_stage, dec_launches = timed(lambda: codec.decode_device(payload, offsets, g, out_px), args.steps,
+                                                args.warmup, profiled=True)
     clocks = sampler.stop() if rank == 0 else None
     n_bins = codec.last_bin_count()
     ok = bool(torch.equal(out_px, px))

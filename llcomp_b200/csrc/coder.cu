@@ -15,6 +15,8 @@
 // K2b  k_range_pass   the irreducible serial chain: x = range*M + A, renormalise, carry/byte emission.
 //                     No shared-memory state, so every slice of the batch is resident at once; S slices
 //                     share a warp (32/S lanes each) when there are more slices than schedulers.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -180,109 +182,153 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
     return d;
 }
 
-struct RangeEnc {
-    ByteTail t;
-    uint32_t range;
+// One pass of renorm_encoder's loop body (llcomp.hpp:40-55) on the byte side.
+__device__ __forceinline__ void shift_low(ByteTail& t) {
+    // plain byte or carry with nothing deferred: emit held (+1 on carry), latch the next byte
+    if (t.hp < kHpEmpty && (t.low - 0xFF01u) >= 0xFFu) {
+        *t.outp++ = (uint8_t)(t.hp + (t.low >> 16));
+        t.hp = (t.low >> 8) & 0xFFu;
+    } else {
+        t = renorm_slow(t);
+    }
+    t.low = (t.low & 0xFFu) << 8;
+}
 
-    __device__ __forceinline__ void shift_low() {
-        // plain byte or carry with nothing deferred: emit held (+1 on carry), latch the next byte
-        if (t.hp < kHpEmpty && (t.low - 0xFF01u) >= 0xFFu) {
-            *t.outp++ = (uint8_t)(t.hp + (t.low >> 16));
-            t.hp = (t.low >> 8) & 0xFFu;
-        } else {
-            t = renorm_slow(t);
-        }
-        t.low = (t.low & 0xFFu) << 8;
+// One decision the plain way (llcomp.hpp:60-73 in the (M, A) form above); used outside the pipelined loop.
+__device__ __forceinline__ void put_simple(ByteTail& t, uint32_t& range, uint32_t m, uint32_t a, bool is_one) {
+    const uint32_t x = range * m + a;
+    const uint32_t r = x >> 8;
+    if (is_one) t.low += range - r;
+    range = r;
+    if (x < 0x10000u) {                                      // range' < 0x100 (and >= 1): one step renormalises
+        shift_low(t);
+        range = r << 8;
     }
-    // One decision, llcomp.hpp:60-73 in the (M, A) form above; range' >= 1, so one renormalisation step suffices.
-    __device__ __forceinline__ void put(uint32_t m, uint32_t a, bool is_one) {
-        const uint32_t x = range * m + a;
-        const uint32_t r = x >> 8;
-        if (is_one) t.low += range - r;
-        range = r;
-        if (__builtin_expect(r < 0x100u, 0)) {
-            shift_low();
-            range = r << 8;
-        }
-    }
-    __device__ __forceinline__ void put2(uint32_t w) {      // two packed entries
-        put(w & 0xFFu, prmt(w, 0x4449), !(w & 0x8000u));
-        put(prmt(w, 0x4442), prmt(w, 0x444B), (int)w >= 0);
-    }
-    __device__ __forceinline__ void finish() {               // llcomp.hpp:75-81 (range = 0xFF: always renormalises)
-        t.low += 0xFFu; shift_low();
-        shift_low();
-    }
-};
+}
+
+// m, a as above; one = 1 when the decision is a 1 (A is 0x00 then, 0xFF otherwise).
+struct Entry { uint32_t m, a, one; };
+__device__ __forceinline__ Entry entry_lo(uint32_t w) {
+    const uint32_t a = prmt(w, 0x4449);
+    return {w & 0xFFu, a, ~a & 1u};
+}
+__device__ __forceinline__ Entry entry_hi(uint32_t w) {
+    const uint32_t a = prmt(w, 0x444B);
+    return {prmt(w, 0x4442), a, ~a & 1u};
+}
+
+constexpr int kRangeWarps = 4;      // warps per CTA of the range pass: one per scheduler of the SM
 
 template <int S>
-__global__ void __launch_bounds__(32) k_range_pass(const uint16_t* __restrict__ queue,
+__global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t* __restrict__ queue,
                                                    const uint64_t* __restrict__ q_off,
                                                    const unsigned long long* __restrict__ n_bins, Geom g, uint64_t s0,
                                                    uint32_t n_launch, uint8_t* __restrict__ scratch,
                                                    uint32_t* __restrict__ slice_bytes, int* __restrict__ status) {
     constexpr int L = 32 / S;                                // lanes per slice
-    __shared__ uint4 stage[2][32];
+    __shared__ uint4 stage_all[kRangeWarps][2][32];
+    __shared__ __align__(16) uint32_t psum_all[kRangeWarps][S][8];
 
-    const int lane = threadIdx.x, grp = lane / L, sub = lane % L;
-    // slice of this lane group; surplus groups of the last warp shadow the last slice (same bytes, same place)
-    const uint32_t k = min(blockIdx.x * S + grp, n_launch - 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / L, sub = lane % L;
+    uint4 (*stage)[32] = stage_all[warp];
+    // slice of this lane group; surplus groups of the last warps shadow the last slice (same bytes, same place)
+    const uint32_t k = min((blockIdx.x * kRangeWarps + warp) * S + grp, n_launch - 1);
     const uint64_t s = s0 + k;
     const Slice sl = slice_of(g, s);
     const uint4* src = reinterpret_cast<const uint4*>(queue + q_off[s]);
     const uint64_t nb = n_bins[s];
-    uint32_t n_vec = (uint32_t)(nb / 8);                     // whole 8-entry vectors; the rest is the tail
-    uint32_t rest = (uint32_t)(nb % 8);
-    const uint32_t my_blocks = (n_vec + L - 1) / L;
-    const uint32_t n_blocks = __reduce_max_sync(kFull, my_blocks);
+    const uint32_t n_vec = (uint32_t)(nb / 8);               // whole 8-entry vectors of this slice
+    // the pipelined loop runs while every slice of the warp has vectors left; the rest goes one entry at a time
+    const uint32_t n_common = __reduce_min_sync(kFull, n_vec);
 
     uint8_t* const out0 = scratch + scratch_off(sl, s);
     uint8_t* const out_end = out0 + scratch_cap(sl);
-    RangeEnc enc;
-    enc.t.low = 0; enc.range = 0xFF00u; enc.t.hp = kHpEmpty;                    // llcomp.hpp:35
-    enc.t.outp = out0;
+    ByteTail t;
+    t.low = 0; t.hp = kHpEmpty; t.outp = out0;               // llcomp.hpp:35
+    uint32_t range = 0xFF00u;
     bool overflow = false;
-    // A slice that outgrows its scratch stops coding (its remaining vectors are skipped), rewinds so that the
-    // few bytes finish() still writes stay inside the scratch, and raises the overflow status.
+    // A slice that outgrows its scratch stops storing: it rewinds to the start of its scratch (the bytes are
+    // void anyway) and raises the overflow status at the end.
     auto guard = [&](uint32_t upcoming) {
-        if (enc.t.outp + (enc.t.hp >> 9) + upcoming + 8 > out_end) {
-            overflow = true; n_vec = 0; rest = 0; enc.t.outp = out0; enc.t.hp = kHpEmpty;
-        }
+        if (t.outp + (t.hp >> 9) + upcoming + 16 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
     };
 
+    // Per 8-entry vector, two stages.  Stage A is the range recurrence alone, straight-line and branch-free
+    // (x = range*M + A; range' = x < 0x10000 ? x & ~0xFF : x >> 8), with the running sum of the low increments
+    // and a bit mask of the decisions that renormalised computed in its shadow.  Stage B replays the byte/carry
+    // side at those decisions only; its loop runs on a warp-uniform mask (REDUX), so its branches are uniform.
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    uint4 r0 = sub < n_vec ? src[sub] : zero4;
-    uint4 r1 = L + sub < n_vec ? src[L + sub] : zero4;
+    uint4 r0 = sub < n_common ? src[sub] : zero4;
+    uint4 r1 = L + sub < n_common ? src[L + sub] : zero4;
+    const uint32_t n_blocks = (n_common + L - 1) / L;
+    uint32_t* const my_psum = &psum_all[warp][grp][0];
     for (uint32_t b = 0; b < n_blocks; ++b) {
         stage[b & 1][lane] = r0;
         __syncwarp();
         r0 = r1;
         {
             const uint64_t v = (uint64_t)(b + 2) * L + sub;             // two refills ahead of the chain
-            r1 = v < n_vec ? src[v] : zero4;
+            r1 = v < n_common ? src[v] : zero4;
         }
-        guard(L * 8);     // a block emits at most one byte per decision plus the bytes deferred so far
+        guard(L * 8);         // a block emits at most one byte per decision plus the bytes deferred so far
+        const int jn = min((uint32_t)L, n_common - b * L);
 #pragma unroll 1
-        for (int j = 0; j < L; ++j) {
-            if (b * L + j < n_vec) {
-                const uint4 w = stage[b & 1][grp * L + j];
-                enc.put2(w.x); enc.put2(w.y); enc.put2(w.z); enc.put2(w.w);
+        for (int j = 0; j < jn; ++j) {
+            const uint4 w = stage[b & 1][grp * L + j];
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            uint32_t psum[8];
+            uint32_t acc = 0, mask = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                                 // stage A
+                const Entry e = (i & 1) ? entry_hi(ww[i >> 1]) : entry_lo(ww[i >> 1]);
+                const uint32_t x = range * e.m + e.a;
+                const uint32_t r = x >> 8;
+                acc += (range - r) * e.one;
+                psum[i] = acc;
+                const bool renorm = x < 0x10000u;
+                mask |= renorm ? (1u << i) : 0u;
+                range = renorm ? (x & 0xFFFFFF00u) : r;
             }
+            uint32_t todo = __reduce_or_sync(kFull, mask);                // uniform: union over the warp's slices
+            if (todo) {                                                   // stage B
+                *reinterpret_cast<uint4*>(my_psum) = make_uint4(psum[0], psum[1], psum[2], psum[3]);
+                *reinterpret_cast<uint4*>(my_psum + 4) = make_uint4(psum[4], psum[5], psum[6], psum[7]);
+                __syncwarp();
+                uint32_t rebase = t.low;                                  // low == rebase + psum[.] between renorms
+                do {
+                    const int i = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (S == 1 || ((mask >> i) & 1u)) {
+                        const uint32_t p = my_psum[i];
+                        t.low = rebase + p;
+                        shift_low(t);
+                        rebase = t.low - p;
+                    }
+                } while (todo);
+                t.low = rebase;
+                __syncwarp();
+            }
+            t.low += acc;
         }
     }
-    // tail: the nb % 8 entries of the last, partial vector
+
+    // the entries beyond the common part (other slices of the warp were shorter, and the nb % 8 tail)
     {
-        const uint16_t* tq = reinterpret_cast<const uint16_t*>(src + n_vec);
-        guard(8);
-        for (uint32_t i = 0; i < rest; ++i) {
+        const uint16_t* tq = reinterpret_cast<const uint16_t*>(src) + (uint64_t)n_common * 8;
+        const uint64_t left = nb - (uint64_t)n_common * 8;
+        for (uint64_t i = 0; i < left; ++i) {
+            if ((i & 63) == 0) guard(64);
             const uint32_t e = tq[i];
-            enc.put(e & 0xFFu, (e & 0x8000u) ? 255u : 0u, !(e & 0x8000u));
+            put_simple(t, range, e & 0xFFu, (e & 0x8000u) ? 255u : 0u, !(e & 0x8000u));
         }
     }
     guard(0);
-    enc.finish();                                                         // llcomp.hpp:449
-    if (sub == 0) {
-        slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(enc.t.outp - out0);
+    // finish(), llcomp.hpp:75-81: range = 0xFF both times, so each renorm_encoder call shifts exactly once
+    t.low += 0xFFu;
+    shift_low(t);
+    shift_low(t);
+    if (sub == 0) {                                                       // shadows write the same value
+        slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(t.outp - out0);
         if (overflow) atomicCAS(status, kDevOk, kDevOverflow);
     }
 }
@@ -303,12 +349,20 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
                               const Geom& g, uint64_t s0, uint64_t count, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                               int* d_status, cudaStream_t st) {
     if (count == 0 || count > 0x3FFFFFFFull) return cudaErrorInvalidValue;
-    // one slice per warp while every warp can have a scheduler of its own (4 x 148 of them); beyond that,
-    // slices share warps: the chain is latency-bound, so a second slice in the same warp is nearly free
+    // One slice per warp while every warp can have a scheduler of its own (4 x 148 of them); beyond that slices
+    // share warps: the chain is latency-bound, so a second slice in the same warp is nearly free.
     const unsigned n = (unsigned)count;
-    if (n <= 592) k_range_pass<1><<<n, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
-    else if (n <= 1184) k_range_pass<2><<<(n + 1) / 2, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
-    else k_range_pass<4><<<(n + 3) / 4, 32, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status);
+    int S = n <= 592 ? 1 : n <= 1184 ? 2 : 4;
+    if (const char* e = getenv("LLCOMP_RANGE_S")) S = atoi(e);            // tuning knob
+    const unsigned per_cta = kRangeWarps * S, ctas = (n + per_cta - 1) / per_cta;
+    const dim3 blk(32 * kRangeWarps);
+    switch (S) {
+        case 1: k_range_pass<1><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
+        case 2: k_range_pass<2><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
+        case 4: k_range_pass<4><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
+        case 8: k_range_pass<8><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
