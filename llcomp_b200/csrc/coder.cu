@@ -219,7 +219,7 @@ __device__ __forceinline__ Entry entry_hi(uint32_t w) {
 
 constexpr int kRangeWarps = 4;      // warps per CTA of the range pass: one per scheduler of the SM
 
-template <int S>
+template <int S, int ACT = 32>
 __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t* __restrict__ queue,
                                                    const uint64_t* __restrict__ q_off,
                                                    const unsigned long long* __restrict__ n_bins, Geom g, uint64_t s0,
@@ -230,6 +230,8 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
     __shared__ __align__(16) uint32_t psum_all[kRangeWarps][S][8];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / L, sub = lane % L;
+    if (lane >= ACT) return;                                 // experiment: the surplus lanes are redundant for S == 1
+    constexpr unsigned kAct = ACT == 32 ? 0xFFFFFFFFu : ((1u << ACT) - 1u);
     uint4 (*stage)[32] = stage_all[warp];
     // slice of this lane group; surplus groups of the last warps shadow the last slice (same bytes, same place)
     const uint32_t k = min((blockIdx.x * kRangeWarps + warp) * S + grp, n_launch - 1);
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
     const uint64_t nb = n_bins[s];
     const uint32_t n_vec = (uint32_t)(nb / 8);               // whole 8-entry vectors of this slice
     // the pipelined loop runs while every slice of the warp has vectors left; the rest goes one entry at a time
-    const uint32_t n_common = __reduce_min_sync(kFull, n_vec);
+    const uint32_t n_common = __reduce_min_sync(kAct, n_vec);
 
     uint8_t* const out0 = scratch + scratch_off(sl, s);
     uint8_t* const out_end = out0 + scratch_cap(sl);
@@ -258,17 +260,25 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
     // and a bit mask of the decisions that renormalised computed in its shadow.  Stage B replays the byte/carry
     // side at those decisions only; its loop runs on a warp-uniform mask (REDUX), so its branches are uniform.
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    uint4 r0 = sub < n_common ? src[sub] : zero4;
-    uint4 r1 = L + sub < n_common ? src[L + sub] : zero4;
+    constexpr int PER = 32 / ACT;                            // vectors each active lane stages per refill
+    uint4 r0[PER], r1[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const uint32_t v0 = sub + q * ACT;
+        r0[q] = v0 < n_common && v0 < (uint32_t)L ? src[v0] : zero4;
+        r1[q] = L + v0 < n_common && v0 < (uint32_t)L ? src[L + v0] : zero4;
+    }
     const uint32_t n_blocks = (n_common + L - 1) / L;
     uint32_t* const my_psum = &psum_all[warp][grp][0];
     for (uint32_t b = 0; b < n_blocks; ++b) {
-        stage[b & 1][lane] = r0;
-        __syncwarp();
-        r0 = r1;
-        {
-            const uint64_t v = (uint64_t)(b + 2) * L + sub;             // two refills ahead of the chain
-            r1 = v < n_common ? src[v] : zero4;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) stage[b & 1][lane + q * ACT] = r0[q];
+        __syncwarp(kAct);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            r0[q] = r1[q];
+            const uint64_t v = (uint64_t)(b + 2) * L + sub + q * ACT;   // two refills ahead of the chain
+            r1[q] = v < n_common && sub + q * ACT < L ? src[v] : zero4;
         }
         guard(L * 8);         // a block emits at most one byte per decision plus the bytes deferred so far
         const int jn = min((uint32_t)L, n_common - b * L);
@@ -289,11 +299,11 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
                 mask |= renorm ? (1u << i) : 0u;
                 range = renorm ? (x & 0xFFFFFF00u) : r;
             }
-            uint32_t todo = __reduce_or_sync(kFull, mask);                // uniform: union over the warp's slices
+            uint32_t todo = __reduce_or_sync(kAct, mask);                // uniform: union over the warp's slices
             if (todo) {                                                   // stage B
                 *reinterpret_cast<uint4*>(my_psum) = make_uint4(psum[0], psum[1], psum[2], psum[3]);
                 *reinterpret_cast<uint4*>(my_psum + 4) = make_uint4(psum[4], psum[5], psum[6], psum[7]);
-                __syncwarp();
+                __syncwarp(kAct);
                 uint32_t rebase = t.low;                                  // low == rebase + psum[.] between renorms
                 do {
                     const int i = __ffs(todo) - 1;
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
                     }
                 } while (todo);
                 t.low = rebase;
-                __syncwarp();
+                __syncwarp(kAct);
             }
             t.low += acc;
         }
@@ -356,6 +366,11 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
     if (const char* e = getenv("LLCOMP_RANGE_S")) S = atoi(e);            // tuning knob
     const unsigned per_cta = kRangeWarps * S, ctas = (n + per_cta - 1) / per_cta;
     const dim3 blk(32 * kRangeWarps);
+    int act = 32;
+    if (const char* e = getenv("LLCOMP_RANGE_ACT")) act = atoi(e);        // experiment
+    if (S == 1 && act == 16) { k_range_pass<1, 16><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); return cudaGetLastError(); }
+    if (S == 1 && act == 8) { k_range_pass<1, 8><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); return cudaGetLastError(); }
+    if (S == 1 && act == 1) { k_range_pass<1, 1><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); return cudaGetLastError(); }
     switch (S) {
         case 1: k_range_pass<1><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
         case 2: k_range_pass<2><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
