@@ -362,7 +362,7 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
     // One slice per warp while every warp can have a scheduler of its own (4 x 148 of them); beyond that slices
     // share warps: the chain is latency-bound, so a second slice in the same warp is nearly free.
     const unsigned n = (unsigned)count;
-    int S = n <= 592 ? 1 : n <= 1184 ? 2 : 4;
+    int S = n <= 1536 ? 1 : n <= 3072 ? 2 : 4;            // measured on B200: ~2 warps per scheduler is the knee
     if (const char* e = getenv("LLCOMP_RANGE_S")) S = atoi(e);            // tuning knob
     const unsigned per_cta = kRangeWarps * S, ctas = (n + per_cta - 1) / per_cta;
     const dim3 blk(32 * kRangeWarps);
