@@ -10,6 +10,8 @@
 // In decode the left neighbour is the sample just reconstructed, so context, bin decode and state
 // update form one serial chain per slice: one CTA (one warp) per slice, lane 0 runs the chain with the
 // 63,408-byte state and (when they fit) the three rows in shared memory.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -152,12 +154,209 @@ __global__ void __launch_bounds__(32) k_slice_decoder(const uint8_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast decoder for 1..4 channels.  Still one serial chain per slice (lane 0), but everything that does not
+// depend on the sample being decoded is taken out of it and given to the whole warp:
+//   * before a row is decoded, the lanes compute for every sample of the row the part of the context hash that
+//     only involves the rows above, 11*q11(tl-t) + 121*q11(t-tr) + 3025*q5(T-t) with the border rules of
+//     llcomp.hpp:495-499, and store it IN PLACE of the row y-2 value it consumed.  That buffer then receives
+//     the reconstructed row y sample by sample, so two row buffers replace the reference's three;
+//   * the payload is staged into a shared-memory ring by all lanes (coalesced), the chain reads bytes from it;
+//   * after a row is decoded, the lanes do the inverse colour transform and the pixel stores.
+// The chain keeps, per plane, l / L / tl in registers (sliding window), fetches the table entries of the
+// sub-states a residual will need together, and updates the 8 sub-states of the context row in registers.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRing = 512;                      // bytes of payload staged ahead of the chain
+constexpr int kChunkSamples = 36;               // samples decoded between two refills (<= 12.4 B each, worst case)
+constexpr int kFastBase = kStateBytes + 128 * 4 + kRing;   // + 2 rows: 76,720 B for a 1024-wide RGB tile -> 3 per SM
+
+struct Q11Lut { int8_t v[256]; };
+constexpr Q11Lut make_q11lut() {
+    Q11Lut t{};
+    for (int i = 0; i < 256; ++i) {
+        const int x = i - 128, a = x < 0 ? -x : x;
+        const int q = (a >= 1) + (a >= 2) + (a >= 5) + (a >= 12) + (a >= 35);
+        t.v[i] = (int8_t)(x < 0 ? -q : q);
+    }
+    return t;
+}
+__constant__ Q11Lut c_q11lut = make_q11lut();
+
+template <int CT>
+__global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __restrict__ payload,
+                                                           const uint64_t* __restrict__ offsets, Geom g,
+                                                           uint8_t* __restrict__ pixels, int* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint2* state = reinterpret_cast<uint2*>(smem);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + kStateBytes);   // P | next_if_0 << 8 | next_if_1 << 16
+    const int8_t* q11lut = c_q11lut.v;
+    uint8_t* ring = smem + kStateBytes + 512;
+
+    const int lane = threadIdx.x;
+    const uint64_t s = blockIdx.x;
+    const Slice sl = slice_of(g, s);
+    const int stride = sl.w * CT;
+    int16_t* bufA = reinterpret_cast<int16_t*>(smem + kFastBase);       // row y-1
+    int16_t* bufB = bufA + ((min(g.tw, g.W) * CT + 7) & ~7);            // row y-2 -> hash part -> row y
+
+    for (int i = lane; i < kStateBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < 128; i += 32) {
+        const uint32_t e = c_tables_dec.entry[i], p = e & 0xFFu, nm = (e >> 8) & 0xFFu, nl = (e >> 16) & 0xFFu;
+        const uint32_t mps = i & 1u;                                     // llcomp.hpp:285, :290-292
+        tab[i] = p | ((mps == 0 ? nm : nl) << 8) | ((mps == 1 ? nm : nl) << 16);
+    }
+
+    const uint8_t* src = payload + offsets[s];
+    const uint32_t len = (uint32_t)(offsets[s + 1] - offsets[s]);
+    uint32_t filled = 0;                                                 // bytes [0, filled) are (or were) in the ring
+    uint32_t pos = 0;                                                    // bytes consumed by the chain (warp-uniform copy)
+    auto refill = [&]() {                                                // zero fill past the end, llcomp.hpp:475-479
+        const uint32_t want = pos + kRing;
+        for (uint32_t k = filled + lane; k < want; k += 32) ring[k & (kRing - 1)] = k < len ? __ldg(src + k) : 0;
+        filled = want;
+        __syncwarp();
+    };
+    refill();
+
+    // decoder registers (meaningful in lane 0)
+    uint32_t low = 0, range = 0xFF00u;                                   // llcomp.hpp:93-96
+    low = ((uint32_t)ring[0] << 8) | ring[1];
+    pos = 2;
+    bool bad = false;
+
+    const size_t pitch = (size_t)g.W * CT;
+    uint8_t* out0 = pixels + (size_t)sl.img * g.H * pitch + (size_t)sl.y0 * pitch + (size_t)sl.x0 * CT;
+
+    for (int h = 0; h < sl.h; ++h) {
+        // ---- all lanes: hash part from the rows above, in place of row y-2 (llcomp.hpp:495-507)
+        for (int j = lane; j < stride; j += 32) {
+            int pre = 0;
+            if (h > 0) {
+                const int w = j / CT;
+                const int t = bufA[j];
+                const int tl = w > 0 ? bufA[j - CT] : t;
+                const int tr = w < sl.w - 1 ? bufA[j + CT] : t;
+                const int T = h > 1 ? bufB[j] : t;
+                pre = 11 * dq11(tl - t) + 121 * dq11(t - tr) + 3025 * dq5(T - t);
+            }
+            bufB[j] = (int16_t)pre;
+        }
+        __syncwarp();
+
+        // ---- the chain, in chunks so that the ring can be topped up by the whole warp
+        int l[CT], L[CT], tl[CT];
+#pragma unroll
+        for (int i = 0; i < CT; ++i) { l[i] = 128; L[i] = 128; tl[i] = 0; }
+        const int px_per_chunk = kChunkSamples / CT;
+        for (int w0 = 0; w0 < sl.w; w0 += px_per_chunk) {
+            refill();
+            if (lane == 0 && !bad) {
+                auto next_byte = [&]() -> uint32_t { return ring[(pos++) & (kRing - 1)]; };
+                const int w1 = min(sl.w, w0 + px_per_chunk);
+                for (int w = w0; w < w1; ++w) {
+                    const int j = w * CT;
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) {
+                        // neighbours (llcomp.hpp:494-499): first row -> t = tl = l; first column -> l = tl = t
+                        int t = h > 0 ? (int)bufA[j + i] : l[i];
+                        if (w == 0 && h > 0) { l[i] = t; L[i] = t; tl[i] = t; }
+                        const int tli = h > 0 ? tl[i] : l[i];
+                        int hash = (int)bufB[j + i] + q11lut[max(-128, min(127, l[i] - tli)) + 128] +
+                                   605 * dq5(L[i] - l[i]);                                  // :501-507
+                        const int lt = l[i] + t - tli;
+                        const int predict = max(min(l[i], lt), min(max(l[i], lt), t));     // median, :509
+                        const bool neg = hash < 0;                                          // :511-515
+                        hash = abs(hash);
+                        uint2 row = state[hash];
+
+                        // one decision of sub-state byte kB of row half `half` (llcomp.hpp:106-121, :517-523)
+                        auto bin = [&](uint32_t& half, int kB) -> uint32_t {
+                            const uint32_t e = tab[(half >> (8 * kB)) & 0xFFu];
+                            const uint32_t r1 = (range * (e & 0xFFu)) >> 8;
+                            const uint32_t r0v = range - r1;
+                            const uint32_t bit = low >= r0v ? 1u : 0u;
+                            low -= bit ? r0v : 0u;
+                            range = bit ? r1 : r0v;
+                            if (range < 0x100u) { range <<= 8; low = (low << 8) + next_byte(); }   // :98-104
+                            const uint32_t ns = __byte_perm(e, 0, 0x4441 + bit);
+                            half = __byte_perm(half, ns, kB == 0 ? 0x3214 : kB == 1 ? 0x3240 : kB == 2 ? 0x3410 : 0x4210);
+                            return bit;
+                        };
+
+                        int diff = 0;
+                        if (!bin(row.x, 0)) {                                                // :225
+                            int e = 0;                                                       // :227-235, ctx min(1+k,4)
+                            if (bin(row.x, 1)) {
+                                e = 1;
+                                if (bin(row.x, 2)) {
+                                    e = 2;
+                                    if (bin(row.x, 3)) {
+                                        e = 3;
+                                        while (bin(row.y, 0)) {
+                                            if (++e > 31) { bad = true; break; }
+                                        }
+                                    }
+                                }
+                            }
+                            if (bad) break;
+                            uint32_t value = 1;                                              // :237-240
+                            if (e >= 1) value += value + bin(row.y, 1);
+                            for (int k = e - 2; k >= 0; --k) value += value + bin(row.y, 2);
+                            diff = bin(row.y, 3) ? -(int)value : (int)value;                 // :242-245
+                        }
+                        state[hash] = row;
+                        const int cur = (int16_t)(predict + (neg ? -diff : diff));           // :526-529
+                        bufB[j + i] = (int16_t)cur;
+                        L[i] = w == 0 ? cur : l[i];                                          // w == 1: L = l (:496)
+                        l[i] = cur;
+                        tl[i] = t;
+                    }
+                    if (bad) break;
+                }
+            }
+            bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            if (bad) {
+                if (lane == 0) atomicCAS(status, kDevOk, kDevBadExponent);
+                return;
+            }
+        }
+        __syncwarp();
+
+        // ---- all lanes: inverse colour transform, clamp, store (llcomp.hpp:532-543)
+        uint8_t* dst = out0 + (size_t)h * pitch;
+        for (int w = lane; w < sl.w; w += 32) {
+            const int16_t* p = bufB + w * CT;
+            if (CT >= 3) {
+                int r = p[0], gg = p[1], b = p[2];
+                gg -= (r + b) / 4;
+                r += gg;
+                b += gg;
+                dst[w * CT + 0] = (uint8_t)max(0, min(255, r));
+                dst[w * CT + 1] = (uint8_t)max(0, min(255, gg));
+                dst[w * CT + 2] = (uint8_t)max(0, min(255, b));
+                if (CT == 4) dst[w * CT + 3] = (uint8_t)p[3];
+            } else {
+#pragma unroll
+                for (int i = 0; i < CT; ++i) dst[w * CT + i] = (uint8_t)p[i];
+            }
+        }
+        __syncwarp();
+        int16_t* tmp = bufA; bufA = bufB; bufB = tmp;                     // row y becomes row y-1, row y-1 becomes y-2
+    }
+}
+
+static int fast_line_bytes(const Geom& g) { return 2 * (((min(g.tw, g.W) * g.C + 7) & ~7) * 2); }
+static bool fast_decoder_fits(const Geom& g) {
+    return g.C >= 1 && g.C <= 4 && kFastBase + fast_line_bytes(g) <= 200 * 1024;
+}
+
 static bool lines_fit_smem(const Geom& g) {
     return (uint64_t)3 * min(g.tw, g.W) * g.C * 2 <= (uint64_t)kDecMaxLineSmem;
 }
 
 uint64_t decoder_line_scratch_bytes(const Geom& g) {
-    if (lines_fit_smem(g)) return 0;
+    if (fast_decoder_fits(g) || lines_fit_smem(g)) return 0;
     return g.n_slices() * 3ull * min(g.tw, g.W) * g.C * 2ull;
 }
 
@@ -165,13 +364,31 @@ cudaError_t configure_slice_decoder() {
     cudaError_t e = cudaFuncSetAttribute(k_slice_decoder<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kDecBaseSmem + kDecMaxLineSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_slice_decoder<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecBaseSmem);
+    e = cudaFuncSetAttribute(k_slice_decoder<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecBaseSmem);
+    if (e != cudaSuccess) return e;
+    const int fast_max = 200 * 1024;
+    e = cudaFuncSetAttribute(k_slice_decoder_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_decoder_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_decoder_fast<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_decoder_fast<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
+    return e;
 }
 
 cudaError_t launch_slice_decoder(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
                                  uint8_t* d_pixels, int16_t* d_line_scratch, int* d_status, cudaStream_t st) {
     const uint64_t ns = g.n_slices();
     if (ns == 0 || ns > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    if (fast_decoder_fits(g) && !getenv("LLCOMP_DECODER_SIMPLE")) {
+        const int smem = kFastBase + fast_line_bytes(g);
+        const unsigned n = (unsigned)ns;
+        switch (g.C) {
+            case 1: k_slice_decoder_fast<1><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
+            case 2: k_slice_decoder_fast<2><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
+            case 3: k_slice_decoder_fast<3><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
+            default: k_slice_decoder_fast<4><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
+        }
+        return cudaGetLastError();
+    }
     if (lines_fit_smem(g)) {
         const int line_bytes = (3 * min(g.tw, g.W) * g.C * 2 + 15) & ~15;
         k_slice_decoder<true><<<(unsigned)ns, 32, kDecBaseSmem + line_bytes, st>>>(d_payload, d_offsets, g, d_pixels,
