@@ -36,24 +36,37 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 // ---------------------------------------------------------------------------------------------------
 // K2a
 // ---------------------------------------------------------------------------------------------------
-constexpr int kModelSmem = kStateBytes + 256 * 4;
+// The contexts of a slice are split into K classes by hash % K; each class is evolved by its own CTA (one warp)
+// with only its share of the state in shared memory (63,408 / K bytes).  Classes never interact -- a context's
+// state depends on that context's decisions only -- so the K warps of a slice need no synchronisation; each
+// scans all records of the slice (the decision offsets are a prefix sum over all of them) and processes its own.
+// More, smaller CTAs per SM is what hides the shared-memory latency chains of this pass.
+template <int K>
+struct ModelShape {
+    static constexpr int kRows = (kContexts + K - 1) / K;
+    static constexpr int kRowBytes = (kRows * 8 + 15) & ~15;
+    static constexpr int kSmem = kRowBytes + 256 * 4;
+};
 
+template <int K>
 __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ sym, Geom g, uint64_t s0,
                                                    uint16_t* __restrict__ queue,
                                                    const uint64_t* __restrict__ q_off) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint2* state = reinterpret_cast<uint2*>(smem);                         // one 8-byte row per context
-    uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kStateBytes);     // [state*2 + bit] = entry | next << 16
+    constexpr int kRowBytes = ModelShape<K>::kRowBytes;
+    uint2* state = reinterpret_cast<uint2*>(smem);                         // one 8-byte row per context of the class
+    uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kRowBytes);       // [state*2 + bit] = entry | next << 16
 
     const int lane = threadIdx.x;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint64_t s = s0 + blockIdx.x;
+    const uint32_t cls = blockIdx.x % K;
+    const uint64_t s = s0 + blockIdx.x / K;
     const Slice sl = slice_of(g, s);
     const uint32_t* in = sym + sl.sym_off;
     const uint64_t n = sl.n;
     uint16_t* q = queue + q_off[s];
 
-    for (int i = lane; i < kStateBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < kRowBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = lane; i < 256; i += 32) {
         const uint32_t st = i >> 1, b = i & 1, e = c_tables.entry[st];
         const uint32_t p = e & 0xFFu;
@@ -85,13 +98,14 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
             total += __popc(m) << b;
         }
 
-        // lanes with the same context form a chain; its first lane carries the row through the members
-        const uint32_t key = valid ? hash : (0x10000u | lane);
+        // lanes of this class with the same context form a chain; its first lane carries the row through the members
+        const bool mine = valid && (hash % K) == cls;
+        const uint32_t key = mine ? hash : (0x10000u | lane);
         uint32_t members = __match_any_sync(kFull, key);
-        const bool leader = valid && (__ffs(members) - 1 == lane);
-        const int rounds = __reduce_max_sync(kFull, valid ? __popc(members) : 0);
+        const bool leader = mine && (__ffs(members) - 1 == lane);
+        const int rounds = __reduce_max_sync(kFull, mine ? __popc(members) : 0);
         uint2 row = make_uint2(0, 0);
-        if (leader) row = state[hash];
+        if (leader) row = state[hash / K];
         uint32_t s0b = row.x & 0xFFu, s1b = (row.x >> 8) & 0xFFu, s2b = (row.x >> 16) & 0xFFu, s3b = row.x >> 24;
         uint32_t s4b = row.y & 0xFFu, s5b = (row.y >> 8) & 0xFFu, s6b = (row.y >> 16) & 0xFFu, s7b = row.y >> 24;
 
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
             }
         }
         if (leader)
-            state[hash] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
+            state[hash / K] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
                                      s4b | (s5b << 8) | (s6b << 16) | (s7b << 24));
         __syncwarp();
         q += total;
@@ -345,13 +359,25 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
 
 // ---------------------------------------------------------------------------------------------------
 cudaError_t configure_slice_coder() {
-    return cudaFuncSetAttribute(k_model_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, kModelSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_model_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<1>::kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_model_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<2>::kSmem);
+    return e;
 }
 
 cudaError_t launch_model_pass(const uint32_t* d_sym, const Geom& g, uint64_t s0, uint64_t count, uint16_t* d_queue,
                               const uint64_t* d_qoff, cudaStream_t st) {
-    if (count == 0 || count > 0x3FFFFFFFull) return cudaErrorInvalidValue;
-    k_model_pass<<<(unsigned)count, 32, kModelSmem, st>>>(d_sym, g, s0, d_queue, d_qoff);
+    if (count == 0 || count > 0x0FFFFFFFull) return cudaErrorInvalidValue;
+    int K = 4;
+    if (const char* e = getenv("LLCOMP_MODEL_K")) K = atoi(e);            // tuning knob
+    const unsigned n = (unsigned)count;
+    switch (K) {
+        case 1: k_model_pass<1><<<n, 32, ModelShape<1>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
+        case 2: k_model_pass<2><<<n * 2, 32, ModelShape<2>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
+        case 4: k_model_pass<4><<<n * 4, 32, ModelShape<4>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
+        case 8: k_model_pass<8><<<n * 8, 32, ModelShape<8>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
+        case 16: k_model_pass<16><<<n * 16, 32, ModelShape<16>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

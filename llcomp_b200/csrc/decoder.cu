@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
     // decoder registers (meaningful in lane 0)
     uint32_t low = 0, range = 0xFF00u;                                   // llcomp.hpp:93-96
     low = ((uint32_t)ring[0] << 8) | ring[1];
-    pos = 2;
+    pos = 2;                                                             // ring[pos] is the next unread byte ...
+    uint32_t nextb = ring[2];                                            // ... and lane 0 keeps it in a register
     bool bad = false;
 
     const size_t pitch = (size_t)g.W * CT;
@@ -251,48 +252,66 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
         for (int w0 = 0; w0 < sl.w; w0 += px_per_chunk) {
             refill();
             if (lane == 0 && !bad) {
-                auto next_byte = [&]() -> uint32_t { return ring[(pos++) & (kRing - 1)]; };
+                nextb = ring[pos & (kRing - 1)];                         // the ring may have been topped up
                 const int w1 = min(sl.w, w0 + px_per_chunk);
                 for (int w = w0; w < w1; ++w) {
                     const int j = w * CT;
+                    // Contexts of all planes of this pixel first: they depend on the previous pixels only, so
+                    // their arithmetic overlaps (llcomp.hpp:494-515); the decode below is the serial part.
+                    int tv[CT], hashv[CT], predv[CT];
 #pragma unroll
                     for (int i = 0; i < CT; ++i) {
-                        // neighbours (llcomp.hpp:494-499): first row -> t = tl = l; first column -> l = tl = t
-                        int t = h > 0 ? (int)bufA[j + i] : l[i];
+                        // neighbours: first row -> t = tl = l; first column -> l = L = tl = t
+                        const int t = h > 0 ? (int)bufA[j + i] : l[i];
                         if (w == 0 && h > 0) { l[i] = t; L[i] = t; tl[i] = t; }
                         const int tli = h > 0 ? tl[i] : l[i];
-                        int hash = (int)bufB[j + i] + q11lut[max(-128, min(127, l[i] - tli)) + 128] +
+                        hashv[i] = (int)bufB[j + i] + q11lut[max(-128, min(127, l[i] - tli)) + 128] +
                                    605 * dq5(L[i] - l[i]);                                  // :501-507
                         const int lt = l[i] + t - tli;
-                        const int predict = max(min(l[i], lt), min(max(l[i], lt), t));     // median, :509
-                        const bool neg = hash < 0;                                          // :511-515
-                        hash = abs(hash);
+                        predv[i] = max(min(l[i], lt), min(max(l[i], lt), t));              // median, :509
+                        tv[i] = t;
+                    }
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) {
+                        const int t = tv[i], predict = predv[i];
+                        const bool neg = hashv[i] < 0;                                      // :511-515
+                        const int hash = abs(hashv[i]);
                         uint2 row = state[hash];
 
-                        // one decision of sub-state byte kB of row half `half` (llcomp.hpp:106-121, :517-523)
-                        auto bin = [&](uint32_t& half, int kB) -> uint32_t {
-                            const uint32_t e = tab[(half >> (8 * kB)) & 0xFFu];
+                        // Table entries of the sub-states a residual can touch once, fetched together so that
+                        // their shared-memory latency overlaps (ctx 4 and 6 repeat: fetched when reached).
+                        const uint32_t e0 = tab[row.x & 0xFFu], e1 = tab[(row.x >> 8) & 0xFFu];
+                        const uint32_t e2 = tab[(row.x >> 16) & 0xFFu], e3 = tab[row.x >> 24];
+                        const uint32_t e5 = tab[(row.y >> 8) & 0xFFu], e7 = tab[row.y >> 24];
+
+                        // one decision with table entry e of sub-state byte kB of `half` (llcomp.hpp:106-121, :517-523)
+                        auto bin = [&](uint32_t e, uint32_t& half, int kB) -> uint32_t {
                             const uint32_t r1 = (range * (e & 0xFFu)) >> 8;
                             const uint32_t r0v = range - r1;
                             const uint32_t bit = low >= r0v ? 1u : 0u;
-                            low -= bit ? r0v : 0u;
+                            low = min(low, low - r0v);                   // low - r0v wraps above low when low < r0v
                             range = bit ? r1 : r0v;
-                            if (range < 0x100u) { range <<= 8; low = (low << 8) + next_byte(); }   // :98-104
+                            if (range < 0x100u) {                                            // :98-104
+                                range <<= 8;
+                                low = (low << 8) + nextb;
+                                ++pos;
+                                nextb = ring[pos & (kRing - 1)];                             // needed at the NEXT refill
+                            }
                             const uint32_t ns = __byte_perm(e, 0, 0x4441 + bit);
                             half = __byte_perm(half, ns, kB == 0 ? 0x3214 : kB == 1 ? 0x3240 : kB == 2 ? 0x3410 : 0x4210);
                             return bit;
                         };
 
                         int diff = 0;
-                        if (!bin(row.x, 0)) {                                                // :225
+                        if (!bin(e0, row.x, 0)) {                                            // :225
                             int e = 0;                                                       // :227-235, ctx min(1+k,4)
-                            if (bin(row.x, 1)) {
+                            if (bin(e1, row.x, 1)) {
                                 e = 1;
-                                if (bin(row.x, 2)) {
+                                if (bin(e2, row.x, 2)) {
                                     e = 2;
-                                    if (bin(row.x, 3)) {
+                                    if (bin(e3, row.x, 3)) {
                                         e = 3;
-                                        while (bin(row.y, 0)) {
+                                        while (bin(tab[row.y & 0xFFu], row.y, 0)) {
                                             if (++e > 31) { bad = true; break; }
                                         }
                                     }
@@ -300,9 +319,9 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
                             }
                             if (bad) break;
                             uint32_t value = 1;                                              // :237-240
-                            if (e >= 1) value += value + bin(row.y, 1);
-                            for (int k = e - 2; k >= 0; --k) value += value + bin(row.y, 2);
-                            diff = bin(row.y, 3) ? -(int)value : (int)value;                 // :242-245
+                            if (e >= 1) value += value + bin(e5, row.y, 1);
+                            for (int k = e - 2; k >= 0; --k) value += value + bin(tab[(row.y >> 16) & 0xFFu], row.y, 2);
+                            diff = bin(e7, row.y, 3) ? -(int)value : (int)value;             // :242-245
                         }
                         state[hash] = row;
                         const int cur = (int16_t)(predict + (neg ? -diff : diff));           // :526-529
