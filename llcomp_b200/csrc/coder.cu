@@ -358,6 +358,189 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2b, warp-specialised form (one CTA of two warps per slice).
+//   chain warp   only the range recurrence x = range*M + A; range' = x < 0x10000 ? x & ~0xFF : x >> 8, four
+//                instructions per decision, operands pre-expanded to (M, A) pairs in shared memory, x written
+//                back to shared memory.  This is the irreducible serial dependency of the encoder.
+//   helper warp  everything else, lane-parallel over 32 decisions at a time: expands the next block of queue
+//                entries; from the x values of the previous block derives range-before/after, the low
+//                increments (segmented sums between renormalisations), low at every renormalisation
+//                (low_j = ((S_{j-1} & 0xFF) << 8) + S_j, because low mod 256 only depends on the last segment),
+//                and feeds those through the byte/carry machine of renorm_encoder (llcomp.hpp:38-58).
+// One __syncthreads per 256-decision block; both rings are double buffered.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBlk = 256;                                    // decisions per block
+
+__device__ __forceinline__ void pair_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+__global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restrict__ queue,
+                                                      const uint64_t* __restrict__ q_off,
+                                                      const unsigned long long* __restrict__ n_bins, Geom g, uint64_t s0,
+                                                      uint8_t* __restrict__ scratch, uint32_t* __restrict__ slice_bytes,
+                                                      int* __restrict__ status, int debug_skip) {
+    __shared__ __align__(16) uint2 in_ring[2][kBlk + 4];     // (M, A) per decision (+ slack for the look-ahead load)
+    __shared__ __align__(16) uint32_t x_ring[2][kBlk];       // x per decision
+
+    // Four warp slots per CTA, two used: which two rotates with the CTA index so that the chain warps of the
+    // CTAs sharing an SM spread over its four schedulers (warp slot w of a CTA issues on scheduler w).
+    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+    const int chain_slot = blockIdx.x & 3, helper_slot = (blockIdx.x + 2) & 3;
+    if (wslot != chain_slot && wslot != helper_slot) return;
+    const bool is_chain = wslot == chain_slot;
+    const uint64_t s = s0 + blockIdx.x;
+    const Slice sl = slice_of(g, s);
+    const uint16_t* q = queue + q_off[s];
+    const uint64_t nb = n_bins[s];
+    const uint32_t n_blk = (uint32_t)((nb + kBlk - 1) / kBlk);
+
+    // helper state
+    uint8_t* const out0 = scratch + scratch_off(sl, s);
+    uint8_t* const out_end = out0 + scratch_cap(sl);
+    ByteTail t;
+    t.low = 0; t.hp = kHpEmpty; t.outp = out0;               // llcomp.hpp:35
+    bool overflow = false;
+    uint32_t x_carry = 0xFF00u << 8;                         // pseudo-x whose successor range is the initial 0xFF00
+    // chain state
+    uint32_t range = 0xFF00u;
+
+    auto load_entries = [&](uint32_t b) -> uint4 {          // lane's 8 entries of block b (0 beyond the end)
+        const uint64_t first = (uint64_t)b * kBlk + lane * 8;
+        if (first + 8 <= nb) return reinterpret_cast<const uint4*>(q)[first / 8];
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; ++k)
+            if (first + k < nb) w[k >> 1] |= (uint32_t)q[first + k] << (16 * (k & 1));
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    };
+    auto expand = [&](uint4 e, int buf) {                    // 8 entries -> 8 (M, A) pairs
+        const uint32_t w[4] = {e.x, e.y, e.z, e.w};
+        uint4* dst = reinterpret_cast<uint4*>(&in_ring[buf][lane * 8]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            dst[k] = make_uint4(w[k] & 0xFFu, prmt(w[k], 0x4449), prmt(w[k], 0x4442), prmt(w[k], 0x444B));
+    };
+
+    uint4 e_next = make_uint4(0, 0, 0, 0);
+    if (!is_chain) {
+        if (n_blk > 0) expand(load_entries(0), 0);
+        if (n_blk > 1) e_next = load_entries(1);
+    }
+    pair_sync();
+
+    for (uint32_t b = 0; b <= n_blk; ++b) {                  // iteration b: chain on block b, helper on block b-1
+        if (is_chain) {
+            if (b < n_blk && debug_skip != 1) {
+                const uint32_t cnt = (uint32_t)min((uint64_t)kBlk, nb - (uint64_t)b * kBlk);
+                const uint4* in = reinterpret_cast<const uint4*>(in_ring[b & 1]);
+                uint4* xo = reinterpret_cast<uint4*>(x_ring[b & 1]);
+                const uint32_t n4 = (cnt + 3) / 4;           // garbage beyond cnt is computed and ignored
+                // operands of the next 4 decisions are fetched while the current 4 run (the ring has slack)
+                uint4 p0 = in[0], p1 = in[1];
+#pragma unroll 4
+                for (uint32_t v = n4; v > 0; --v) {
+                    in += 2;
+                    const uint4 q0 = in[0], q1 = in[1];
+                    uint4 xs;
+                    xs.x = range * p0.x + p0.y; range = xs.x < 0x10000u ? (xs.x & 0xFFFFFF00u) : (xs.x >> 8);
+                    xs.y = range * p0.z + p0.w; range = xs.y < 0x10000u ? (xs.y & 0xFFFFFF00u) : (xs.y >> 8);
+                    xs.z = range * p1.x + p1.y; range = xs.z < 0x10000u ? (xs.z & 0xFFFFFF00u) : (xs.z >> 8);
+                    xs.w = range * p1.z + p1.w; range = xs.w < 0x10000u ? (xs.w & 0xFFFFFF00u) : (xs.w >> 8);
+                    *xo++ = xs;
+                    p0 = q0; p1 = q1;
+                }
+            }
+        } else {
+            if (b > 0 && debug_skip != 2) {                  // byte side of block b-1
+                const uint32_t pb = b - 1;
+                const uint32_t cnt = (uint32_t)min((uint64_t)kBlk, nb - (uint64_t)pb * kBlk);
+                const uint32_t* xr = x_ring[pb & 1];
+                const uint2* inr = in_ring[pb & 1];
+                for (uint32_t base = 0; base < cnt; base += 32) {
+                    const bool live = base + lane < cnt;
+                    const uint32_t x = live ? xr[base + lane] : 0x01000000u;      // inert: no renorm, delta 0
+                    const uint32_t a = live ? inr[base + lane].y : 255u;
+                    uint32_t xp = __shfl_up_sync(kFull, x, 1);
+                    if (lane == 0) xp = x_carry;
+                    x_carry = __shfl_sync(kFull, x, 31);
+                    const bool any_dead = __any_sync(kFull, !live);
+                    if (any_dead) {                          // keep the carry at the last live decision
+                        const uint32_t last = cnt - base - 1;
+                        x_carry = __shfl_sync(kFull, x, last);
+                    }
+                    const uint32_t r_before = xp < 0x10000u ? (xp & 0xFFFFFF00u) : (xp >> 8);
+                    const uint32_t delta = (live && a == 0) ? r_before - (x >> 8) : 0u;
+                    const uint32_t F = __ballot_sync(kFull, live && x < 0x10000u);   // renormalising decisions
+                    uint32_t pre = delta;                    // inclusive prefix sum of the low increments
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(kFull, pre, d);
+                        if (lane >= d) pre += y;
+                    }
+                    const uint32_t total = __shfl_sync(kFull, pre, 31);
+                    if (F == 0) { t.low += total; continue; }
+                    // segment sums: segment of lane i starts after the last renormalisation below i
+                    const uint32_t below = F & ((1u << lane) - 1u);
+                    const int p = below ? 31 - __clz(below) : -1;           // previous renormalising lane
+                    const uint32_t pre_p = __shfl_sync(kFull, pre, p < 0 ? 0 : p);
+                    const uint32_t seg = pre - (p < 0 ? 0u : pre_p);         // S_j when lane renormalises
+                    const int first = __ffs(F) - 1;
+                    // low at this lane's renormalisation (valid on lanes of F)
+                    const uint32_t seg_p = __shfl_sync(kFull, seg, p < 0 ? 0 : p);
+                    const uint32_t low_first_part = t.low;                   // low entering the sub-block
+                    uint32_t low_ev;
+                    if (p < 0) low_ev = low_first_part + seg;
+                    else low_ev = (((seg_p + (p == first ? low_first_part : 0u)) & 0xFFu) << 8) + seg;
+                    // feed the renormalisations through the byte/carry machine (llcomp.hpp:40-55)
+                    if (t.outp + (t.hp >> 9) + 32 + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
+                    const bool is_ev = (F >> lane) & 1u;
+                    const int last_lane = 31 - __clz(F);
+                    // Plain regime: a byte is latched, nothing is deferred, and no renormalisation of this sub-block
+                    // defers one (low in 0xFF01..0xFFFF).  Then renormalisation j emits the byte latched by j-1 plus
+                    // its own carry, independently of all the others: every lane writes its own byte.
+                    const bool defers = is_ev && (low_ev - 0xFF01u) < 0xFFu;
+                    if (t.hp < kHpEmpty && !__any_sync(kFull, defers)) {
+                        const uint32_t low_p = __shfl_sync(kFull, low_ev, p < 0 ? 0 : p);
+                        const uint32_t held = p < 0 ? t.hp : (low_p >> 8) & 0xFFu;
+                        if (is_ev) t.outp[__popc(below)] = (uint8_t)(held + (low_ev >> 16));
+                        const uint32_t low_last = __shfl_sync(kFull, low_ev, last_lane);
+                        t.outp += __popc(F);
+                        t.hp = (low_last >> 8) & 0xFFu;
+                        t.low = (low_last & 0xFFu) << 8;
+                    } else {
+                        uint32_t todo = F;
+                        do {
+                            const int i = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            t.low = __shfl_sync(kFull, low_ev, i);
+                            shift_low(t);
+                        } while (todo);
+                    }
+                    // decisions after the last renormalisation of the sub-block
+                    const uint32_t pre_last = __shfl_sync(kFull, pre, last_lane);
+                    t.low += total - pre_last;
+                }
+            }
+            if (b + 1 < n_blk) {                             // operands of block b+1, entries of block b+2
+                expand(e_next, (b + 1) & 1);
+                if (b + 2 < n_blk) e_next = load_entries(b + 2);
+            }
+        }
+        pair_sync();
+    }
+
+    if (!is_chain) {
+        if (t.outp + (t.hp >> 9) + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
+        // finish(), llcomp.hpp:75-81: range = 0xFF both times, so each renorm_encoder call shifts exactly once
+        t.low += 0xFFu;
+        shift_low(t);
+        shift_low(t);
+        if (lane == 0) {
+            slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(t.outp - out0);
+            if (overflow) atomicCAS(status, kDevOk, kDevOverflow);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 cudaError_t configure_slice_coder() {
     cudaError_t e = cudaFuncSetAttribute(k_model_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<1>::kSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_model_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<2>::kSmem);
@@ -388,6 +571,12 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
     // One slice per warp while every warp can have a scheduler of its own (4 x 148 of them); beyond that slices
     // share warps: the chain is latency-bound, so a second slice in the same warp is nearly free.
     const unsigned n = (unsigned)count;
+    if (!getenv("LLCOMP_RANGE_LOCKSTEP")) {                               // default: warp-specialised form
+        int skip = 0;                                                      // timing experiments only (1: no chain, 2: no byte side)
+        if (const char* e = getenv("LLCOMP_WS_SKIP")) skip = atoi(e);
+        k_range_pass_ws<<<n, 128, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, d_scratch, d_slice_bytes, d_status, skip);
+        return cudaGetLastError();
+    }
     int S = n <= 1536 ? 1 : n <= 3072 ? 2 : 4;            // measured on B200: ~2 warps per scheduler is the knee
     if (const char* e = getenv("LLCOMP_RANGE_S")) S = atoi(e);            // tuning knob
     const unsigned per_cta = kRangeWarps * S, ctas = (n + per_cta - 1) / per_cta;
