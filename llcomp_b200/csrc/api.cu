@@ -68,6 +68,7 @@ struct llcomp_ctx {
     DevBuf<uint8_t> scratch;                // K2b per-slice payloads before compaction
     DevBuf<uint32_t> slice_bytes;
     DevBuf<int16_t> lines;                  // K5 row scratch when a tile row does not fit in smem
+    DevBuf<uint8_t> gstate;                 // per-slice state rows when they live in global memory (behind L1)
     DevBuf<uint8_t> pixels, payload;        // staging of the host-buffer entry points
     DevBuf<uint64_t> offsets;
     int* d_status = nullptr;
@@ -244,6 +245,7 @@ void llcomp_b200_ctx_destroy(llcomp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->sym.release(); ctx->scratch.release(); ctx->slice_bytes.release(); ctx->lines.release();
     ctx->pixels.release(); ctx->payload.release(); ctx->offsets.release();
+    ctx->gstate.release();
     ctx->slice_bins.release(); ctx->qoff.release(); ctx->queue.release(); ctx->h_bins.release(); ctx->h_qoff.release();
     if (ctx->d_status) cudaFree(ctx->d_status);
     for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
@@ -367,10 +369,12 @@ int llcomp_b200_decode_device(llcomp_ctx* ctx, const uint8_t* d_payload, const u
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const uint64_t lb = decoder_line_scratch_bytes(g);
     if (lb) CK(ctx->lines.reserve(lb / 2));
+    const uint64_t gb = decoder_global_state_bytes(g);
+    if (gb) CK(ctx->gstate.reserve(gb));
     begin_call(ctx);
     {
         StageScope sc(ctx, st, kStDecoder);
-        CK(launch_slice_decoder(d_payload, d_offsets, g, d_pixels, ctx->lines.p, ctx->d_status, st));
+        CK(launch_slice_decoder(d_payload, d_offsets, g, d_pixels, ctx->lines.p, ctx->gstate.p, ctx->d_status, st));
     }
     return LLCOMP_OK;
 }

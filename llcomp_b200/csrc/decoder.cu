@@ -182,24 +182,32 @@ constexpr Q11Lut make_q11lut() {
 }
 __constant__ Q11Lut c_q11lut = make_q11lut();
 
-template <int CT>
+// kGlobalState: the slice's state rows live in global memory (pre-zeroed by the host) and are reached through
+// L1 instead of shared memory.  Measured on B200 (profiles/microbench/l1_rmw.cu): a dependent 8-byte
+// read-modify-write chain costs 116 cycles through L1 against 97 in shared memory, and stores keep the L1 line
+// valid, as long as the hot rows of the SM's slices fit L1.  Without the 63 KB of shared memory per slice, 7+
+// slices fit an SM instead of 3, so a 1024-slice batch decodes in one wave.
+template <int CT, bool kGlobalState>
 __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __restrict__ payload,
                                                            const uint64_t* __restrict__ offsets, Geom g,
-                                                           uint8_t* __restrict__ pixels, int* __restrict__ status) {
+                                                           uint8_t* __restrict__ pixels, int* __restrict__ status,
+                                                           uint2* __restrict__ gstate) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint2* state = reinterpret_cast<uint2*>(smem);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + kStateBytes);   // P | next_if_0 << 8 | next_if_1 << 16
+    constexpr int kStateSmem = kGlobalState ? 0 : kStateBytes;
+    uint2* state = kGlobalState ? gstate + (size_t)blockIdx.x * kContexts : reinterpret_cast<uint2*>(smem);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + kStateSmem);    // P | next_if_0 << 8 | next_if_1 << 16
     const int8_t* q11lut = c_q11lut.v;
-    uint8_t* ring = smem + kStateBytes + 512;
+    uint8_t* ring = smem + kStateSmem + 512;
 
     const int lane = threadIdx.x;
     const uint64_t s = blockIdx.x;
     const Slice sl = slice_of(g, s);
     const int stride = sl.w * CT;
-    int16_t* bufA = reinterpret_cast<int16_t*>(smem + kFastBase);       // row y-1
+    int16_t* bufA = reinterpret_cast<int16_t*>(smem + kStateSmem + 512 + kRing);   // row y-1
     int16_t* bufB = bufA + ((min(g.tw, g.W) * CT + 7) & ~7);            // row y-2 -> hash part -> row y
 
-    for (int i = lane; i < kStateBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (!kGlobalState)
+        for (int i = lane; i < kStateBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = lane; i < 128; i += 32) {
         const uint32_t e = c_tables_dec.entry[i], p = e & 0xFFu, nm = (e >> 8) & 0xFFu, nl = (e >> 16) & 0xFFu;
         const uint32_t mps = i & 1u;                                     // llcomp.hpp:285, :290-292
@@ -369,6 +377,15 @@ static int fast_line_bytes(const Geom& g) { return 2 * (((min(g.tw, g.W) * g.C +
 static bool fast_decoder_fits(const Geom& g) {
     return g.C >= 1 && g.C <= 4 && kFastBase + fast_line_bytes(g) <= 200 * 1024;
 }
+// State in shared memory while every slice of the call finds a shared-memory slot at once (3 per SM for
+// <= 1024-wide RGB tiles), else state in global memory behind L1 (7+ slices per SM, one wave).
+static bool decoder_wants_global_state(const Geom& g) {
+    const int per_sm = (228 * 1024) / (kFastBase + fast_line_bytes(g) + 1024);
+    return fast_decoder_fits(g) && g.n_slices() > (uint64_t)per_sm * 148 && !getenv("LLCOMP_DECODER_SMEM_STATE");
+}
+uint64_t decoder_global_state_bytes(const Geom& g) {
+    return decoder_wants_global_state(g) ? g.n_slices() * (uint64_t)kStateBytes : 0;
+}
 
 static bool lines_fit_smem(const Geom& g) {
     return (uint64_t)3 * min(g.tw, g.W) * g.C * 2 <= (uint64_t)kDecMaxLineSmem;
@@ -386,25 +403,39 @@ cudaError_t configure_slice_decoder() {
     e = cudaFuncSetAttribute(k_slice_decoder<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecBaseSmem);
     if (e != cudaSuccess) return e;
     const int fast_max = 200 * 1024;
-    e = cudaFuncSetAttribute(k_slice_decoder_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_decoder_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_decoder_fast<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_decoder_fast<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max);
+#define LLC_SET(CT, G) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_decoder_fast<CT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_max)
+    LLC_SET(1, false); LLC_SET(2, false); LLC_SET(3, false); LLC_SET(4, false);
+    LLC_SET(1, true); LLC_SET(2, true); LLC_SET(3, true); LLC_SET(4, true);
+#undef LLC_SET
     return e;
 }
 
 cudaError_t launch_slice_decoder(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
-                                 uint8_t* d_pixels, int16_t* d_line_scratch, int* d_status, cudaStream_t st) {
+                                 uint8_t* d_pixels, int16_t* d_line_scratch, uint8_t* d_gstate, int* d_status,
+                                 cudaStream_t st) {
     const uint64_t ns = g.n_slices();
     if (ns == 0 || ns > 0x7FFFFFFFull) return cudaErrorInvalidValue;
     if (fast_decoder_fits(g) && !getenv("LLCOMP_DECODER_SIMPLE")) {
-        const int smem = kFastBase + fast_line_bytes(g);
         const unsigned n = (unsigned)ns;
+        if (decoder_wants_global_state(g)) {
+            const int smem = kFastBase - kStateBytes + fast_line_bytes(g);
+            uint2* gs = reinterpret_cast<uint2*>(d_gstate);
+            cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);   // all states start at 0
+            if (e != cudaSuccess) return e;
+            switch (g.C) {
+                case 1: k_slice_decoder_fast<1, true><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, gs); break;
+                case 2: k_slice_decoder_fast<2, true><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, gs); break;
+                case 3: k_slice_decoder_fast<3, true><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, gs); break;
+                default: k_slice_decoder_fast<4, true><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, gs); break;
+            }
+            return cudaGetLastError();
+        }
+        const int smem = kFastBase + fast_line_bytes(g);
         switch (g.C) {
-            case 1: k_slice_decoder_fast<1><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
-            case 2: k_slice_decoder_fast<2><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
-            case 3: k_slice_decoder_fast<3><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
-            default: k_slice_decoder_fast<4><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status); break;
+            case 1: k_slice_decoder_fast<1, false><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, nullptr); break;
+            case 2: k_slice_decoder_fast<2, false><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, nullptr); break;
+            case 3: k_slice_decoder_fast<3, false><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, nullptr); break;
+            default: k_slice_decoder_fast<4, false><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, nullptr); break;
         }
         return cudaGetLastError();
     }

@@ -26,8 +26,10 @@ cudaError_t launch_compact(const uint8_t* d_scratch, const Geom& g, const uint64
 
 // K5  payloads -> pixels (decoder.cu)
 cudaError_t launch_slice_decoder(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
-                                 uint8_t* d_pixels, int16_t* d_line_scratch, int* d_status,
+                                 uint8_t* d_pixels, int16_t* d_line_scratch, uint8_t* d_gstate, int* d_status,
                                  cudaStream_t st);
+// bytes of global state the decoder wants for this geometry (0 when the state stays in shared memory)
+uint64_t decoder_global_state_bytes(const Geom& g);
 cudaError_t configure_slice_decoder();
 // bytes of global line scratch the decoder needs for this geometry (0 when the rows fit in shared memory)
 uint64_t decoder_line_scratch_bytes(const Geom& g);

@@ -261,6 +261,31 @@ def test_small_queue_budget_forces_launch_groups(codec):
     assert payload[int(off[4]):int(off[5])].cpu().numpy().tobytes() == oracle.encode_tile(imgs[1], 0, 0, 64, 48)
 
 
+def test_many_slices_decode_with_state_behind_l1(codec):
+    """More slices than shared-memory slots (3 x 148): the decoder keeps the state rows in global memory."""
+    import torch
+    imgs = np.stack([oracle.generate(256, 192, 3, 6, 300 + k) for k in range(16)])
+    g = codec.geometry(256, 192, 3, 32, 32, 16)                      # 48 tiles x 16 images = 768 slices
+    assert codec.slice_count(g) == 768
+    d_px = torch.from_numpy(imgs).cuda()
+    payload, offsets = codec.encode_device(d_px, g)
+    codec.finish()
+    out = codec.decode_device(payload, offsets, g)
+    codec.finish()
+    assert torch.equal(out.view(16, 192, 256, 3), d_px)
+    os.environ["LLCOMP_DECODER_SMEM_STATE"] = "1"                     # same answer with the state in shared memory
+    try:
+        out2 = codec.decode_device(payload, offsets, g)
+        codec.finish()
+    finally:
+        del os.environ["LLCOMP_DECODER_SMEM_STATE"]
+    assert torch.equal(out2, out)
+    off = offsets.cpu().numpy()
+    k = 48 * 5 + 17                                                   # one slice against the oracle
+    x0, y0, sw, sh = tiles_of(256, 192, 32, 32)[17]
+    assert payload[int(off[k]):int(off[k + 1])].cpu().numpy().tobytes() == oracle.encode_tile(imgs[5], x0, y0, sw, sh)
+
+
 def test_device_resident_round_trip(codec):
     import torch
     imgs = np.stack([oracle.generate(256, 192, 3, 6, 50 + k) for k in range(5)])
