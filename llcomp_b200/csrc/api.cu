@@ -338,11 +338,14 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
     for (const Group& gr : groups) max_entries = std::max(max_entries, gr.entries);
     CK(ctx->queue.reserve(max_entries + 64));
     CK(cudaMemcpyAsync(ctx->qoff.p, ctx->h_qoff.p, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    uint64_t gstate_bytes = 0;
+    for (const Group& gr : groups) gstate_bytes = std::max(gstate_bytes, model_global_state_bytes(gr.count));
+    if (gstate_bytes) CK(ctx->gstate.reserve(gstate_bytes));
 
     for (const Group& gr : groups) {
         {
             StageScope sc(ctx, st, kStModel);
-            CK(launch_model_pass(ctx->sym.p, g, gr.s0, gr.count, ctx->queue.p, ctx->qoff.p, st));
+            CK(launch_model_pass(ctx->sym.p, g, gr.s0, gr.count, ctx->queue.p, ctx->qoff.p, ctx->gstate.p, st));
         }
         {
             StageScope sc(ctx, st, kStRange);

@@ -48,13 +48,18 @@ struct ModelShape {
     static constexpr int kSmem = kRowBytes + 256 * 4;
 };
 
-template <int K>
+// kGlobalState (K == 1): the rows live in global memory, pre-zeroed by the host, and are reached through L1
+// (116 vs 97 cycles per dependent read-modify-write, profiles/microbench/l1_rmw.cu); without 63 KB of shared
+// memory per slice every slice of a 1024-image batch is resident at once.
+template <int K, bool kGlobalState = false>
 __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ sym, Geom g, uint64_t s0,
                                                    uint16_t* __restrict__ queue,
-                                                   const uint64_t* __restrict__ q_off) {
+                                                   const uint64_t* __restrict__ q_off,
+                                                   uint2* __restrict__ gstate) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kRowBytes = ModelShape<K>::kRowBytes;
-    uint2* state = reinterpret_cast<uint2*>(smem);                         // one 8-byte row per context of the class
+    constexpr int kRowBytes = kGlobalState ? 0 : ModelShape<K>::kRowBytes;
+    uint2* state = kGlobalState ? gstate + (size_t)blockIdx.x * kContexts
+                                : reinterpret_cast<uint2*>(smem);         // one 8-byte row per context of the class
     uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kRowBytes);       // [state*2 + bit] = entry | next << 16
 
     const int lane = threadIdx.x;
@@ -547,18 +552,28 @@ cudaError_t configure_slice_coder() {
     return e;
 }
 
+uint64_t model_global_state_bytes(uint64_t count) {
+    // state in shared memory while every slice of the launch finds a slot (3 per SM), else behind L1
+    return (count > 3 * 148 && !getenv("LLCOMP_MODEL_SMEM_STATE")) ? count * (uint64_t)kStateBytes : 0;
+}
+
 cudaError_t launch_model_pass(const uint32_t* d_sym, const Geom& g, uint64_t s0, uint64_t count, uint16_t* d_queue,
-                              const uint64_t* d_qoff, cudaStream_t st) {
+                              const uint64_t* d_qoff, uint8_t* d_gstate, cudaStream_t st) {
     if (count == 0 || count > 0x0FFFFFFFull) return cudaErrorInvalidValue;
-    int K = 4;
-    if (const char* e = getenv("LLCOMP_MODEL_K")) K = atoi(e);            // tuning knob
     const unsigned n = (unsigned)count;
+    if (model_global_state_bytes(count)) {
+        cudaError_t e = cudaMemsetAsync(d_gstate, 0, count * (uint64_t)kStateBytes, st);   // all states start at 0
+        if (e != cudaSuccess) return e;
+        k_model_pass<1, true><<<n, 32, 256 * 4, st>>>(d_sym, g, s0, d_queue, d_qoff, reinterpret_cast<uint2*>(d_gstate));
+        return cudaGetLastError();
+    }
+    int K = 1;
+    if (const char* e = getenv("LLCOMP_MODEL_K")) K = atoi(e);            // tuning knob (hash-class partition)
     switch (K) {
-        case 1: k_model_pass<1><<<n, 32, ModelShape<1>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
-        case 2: k_model_pass<2><<<n * 2, 32, ModelShape<2>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
-        case 4: k_model_pass<4><<<n * 4, 32, ModelShape<4>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
-        case 8: k_model_pass<8><<<n * 8, 32, ModelShape<8>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
-        case 16: k_model_pass<16><<<n * 16, 32, ModelShape<16>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff); break;
+        case 1: k_model_pass<1><<<n, 32, ModelShape<1>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
+        case 2: k_model_pass<2><<<n * 2, 32, ModelShape<2>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
+        case 4: k_model_pass<4><<<n * 4, 32, ModelShape<4>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
+        case 8: k_model_pass<8><<<n * 8, 32, ModelShape<8>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -12,7 +12,9 @@ cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_
 // K2a records -> bin queue (model pass, state in shared memory); K2b bin queue -> per-slice scratch payloads
 //     and byte counts (range pass).  Both work on slices [s0, s0+count); d_qoff[s] = first queue entry of slice s.
 cudaError_t launch_model_pass(const uint32_t* d_sym, const Geom& g, uint64_t s0, uint64_t count, uint16_t* d_queue,
-                              const uint64_t* d_qoff, cudaStream_t st);
+                              const uint64_t* d_qoff, uint8_t* d_gstate, cudaStream_t st);
+// bytes of global state the model pass wants for a launch of `count` slices (0: state stays in shared memory)
+uint64_t model_global_state_bytes(uint64_t count);
 cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, const unsigned long long* d_nbins,
                               const Geom& g, uint64_t s0, uint64_t count, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                               int* d_status, cudaStream_t st);
