@@ -309,8 +309,8 @@ def main():
     n_samples = raw
     alg = {  # algorithmic bytes per launch = per-sample figure of SURVEY.md 8(d) x samples of one launch
         "frontend": 5 * n_samples,                          # 1 B pixel read + 4 B record written
-        "model_pass": 4 * n_samples + 2 * n_bins,           # records read + 2-byte queue entries written
-        "range_pass": 2 * n_bins + stream_bytes,            # queue read + payload written to scratch
+        "slice_coder": 4 * n_samples + stream_bytes,        # fused coder: records read + payload written to scratch
+        "model_pass": 4 * n_samples + 2 * n_bins,           # (split path only) records read + queue entries written
         "scan": 4 * n_slices + 8 * (n_slices + 1),
         "compact": 2 * stream_bytes,                        # scratch read + contiguous stream written
         "slice_decoder": stream_bytes + n_samples,          # payload read + pixels written
@@ -326,13 +326,13 @@ def main():
     dom = max((k for k in kernels if k["name"] != "slice_decoder"), key=lambda k: k["ms"])
     roofline = {"kernel": dom["name"], "bound": "hbm", "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
-                "note": "range_pass is one serial dependency chain per slice (issue/latency-bound, not HBM-bound); the "
-                        "HBM-bound kernel of the path is `frontend`, listed under kernels[]"}
+                "note": "slice_coder holds one serial dependency chain per slice (issue/latency-bound, not HBM-bound); "
+                        "the HBM-bound kernel of the path is `frontend`, listed under kernels[]"}
 
     line = {"metric": METRIC, "value": world * raw / (enc_ms / 1e3) / 1e9, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": enc_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic", "config": config,
-            "impl": "ours", "round_trip_exact": ok, "bits_per_pixel": bpp, "bins_per_sample": n_bins / raw,
+            "impl": "ours", "round_trip_exact": ok, "bits_per_pixel": bpp, "bins_per_sample": (n_bins / raw) if n_bins else None,
             "decode": {"value": world * raw / (dec_ms / 1e3) / 1e9, "unit": UNIT, "ms_per_step": dec_ms, "e2e": dec_e2e},
             "e2e": e2e, "gpu_launches": enc_launches + dec_launches,
             "gpu_launches_detail": {"encode_steps": enc_launches, "decode_steps": dec_launches},

@@ -19,7 +19,7 @@ using namespace llc;
 namespace {
 
 enum Stage { kStFrontend = 0, kStModel, kStRange, kStScan, kStCompact, kStDecoder };
-const char* const kStageNames[LLCOMP_B200_N_STAGES] = {"frontend", "model_pass", "range_pass", "scan", "compact",
+const char* const kStageNames[LLCOMP_B200_N_STAGES] = {"frontend", "model_pass", "slice_coder", "scan", "compact",
                                                        "slice_decoder"};
 
 template <typename T>
@@ -310,47 +310,62 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
     CK(ctx->h_qoff.reserve(ns));
     begin_call(ctx);
 
-    // K1: records + exact decision count of every slice
-    CK(cudaMemsetAsync(ctx->slice_bins.p, 0, ns * sizeof(unsigned long long), st));
-    {
-        StageScope sc(ctx, st, kStFrontend);
-        CK(launch_frontend(d_pixels, g, ctx->sym.p, ctx->slice_bins.p, st));
-    }
-    // The one host round trip of the encoder: the counts size the bin queue and split the slices into
-    // launch groups that fit the queue budget (one group unless the batch is huge or very noisy).
-    CK(cudaMemcpyAsync(ctx->h_bins.p, ctx->slice_bins.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const uint64_t budget_entries = ctx->queue_budget / 2;
-    struct Group { uint64_t s0, count, entries; };
-    std::vector<Group> groups;
-    uint64_t run = 0, start = 0;
-    ctx->last_bins = 0;
-    for (uint64_t k = 0; k < ns; ++k) {
-        ctx->last_bins += ctx->h_bins.p[k];
-        const uint64_t need = (ctx->h_bins.p[k] + kQueuePad + 7) & ~7ull;
-        if (need > budget_entries) { ctx->last_error = "bin queue budget too small for one slice"; return LLCOMP_ERR_NOMEM; }
-        if (run + need > budget_entries) { groups.push_back({start, k - start, run}); start = k; run = 0; }
-        ctx->h_qoff.p[k] = run;
-        run += need;
-    }
-    groups.push_back({start, ns - start, run});
-    uint64_t max_entries = 0;
-    for (const Group& gr : groups) max_entries = std::max(max_entries, gr.entries);
-    CK(ctx->queue.reserve(max_entries + 64));
-    CK(cudaMemcpyAsync(ctx->qoff.p, ctx->h_qoff.p, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    uint64_t gstate_bytes = 0;
-    for (const Group& gr : groups) gstate_bytes = std::max(gstate_bytes, model_global_state_bytes(gr.count));
-    if (gstate_bytes) CK(ctx->gstate.reserve(gstate_bytes));
-
-    for (const Group& gr : groups) {
+    if (!getenv("LLCOMP_CODER_SPLIT")) {
+        // Default: front end, then ONE fused coder kernel (model + range chain + bytes per slice); fully asynchronous.
         {
-            StageScope sc(ctx, st, kStModel);
-            CK(launch_model_pass(ctx->sym.p, g, gr.s0, gr.count, ctx->queue.p, ctx->qoff.p, ctx->gstate.p, st));
+            StageScope sc(ctx, st, kStFrontend);
+            CK(launch_frontend(d_pixels, g, ctx->sym.p, nullptr, st));
         }
+        const uint64_t gsb = model_global_state_bytes(ns);
+        if (gsb) CK(ctx->gstate.reserve(gsb));
         {
             StageScope sc(ctx, st, kStRange);
-            CK(launch_range_pass(ctx->queue.p, ctx->qoff.p, ctx->slice_bins.p, g, gr.s0, gr.count, ctx->scratch.p,
-                                 ctx->slice_bytes.p, ctx->d_status, st));
+            CK(launch_slice_coder_fused(ctx->sym.p, g, ctx->scratch.p, ctx->slice_bytes.p, ctx->d_status, ctx->gstate.p, st));
+        }
+        ctx->last_bins = 0;
+    } else {
+    // K1: records + exact decision count of every slice
+        CK(cudaMemsetAsync(ctx->slice_bins.p, 0, ns * sizeof(unsigned long long), st));
+        {
+            StageScope sc(ctx, st, kStFrontend);
+            CK(launch_frontend(d_pixels, g, ctx->sym.p, ctx->slice_bins.p, st));
+        }
+        // The one host round trip of the encoder: the counts size the bin queue and split the slices into
+        // launch groups that fit the queue budget (one group unless the batch is huge or very noisy).
+        CK(cudaMemcpyAsync(ctx->h_bins.p, ctx->slice_bins.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint64_t budget_entries = ctx->queue_budget / 2;
+        struct Group { uint64_t s0, count, entries; };
+        std::vector<Group> groups;
+        uint64_t run = 0, start = 0;
+        ctx->last_bins = 0;
+        for (uint64_t k = 0; k < ns; ++k) {
+            ctx->last_bins += ctx->h_bins.p[k];
+            const uint64_t need = (ctx->h_bins.p[k] + kQueuePad + 7) & ~7ull;
+            if (need > budget_entries) { ctx->last_error = "bin queue budget too small for one slice"; return LLCOMP_ERR_NOMEM; }
+            if (run + need > budget_entries) { groups.push_back({start, k - start, run}); start = k; run = 0; }
+            ctx->h_qoff.p[k] = run;
+            run += need;
+        }
+        groups.push_back({start, ns - start, run});
+        uint64_t max_entries = 0;
+        for (const Group& gr : groups) max_entries = std::max(max_entries, gr.entries);
+        CK(ctx->queue.reserve(max_entries + 64));
+        CK(cudaMemcpyAsync(ctx->qoff.p, ctx->h_qoff.p, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        uint64_t gstate_bytes = 0;
+        for (const Group& gr : groups) gstate_bytes = std::max(gstate_bytes, model_global_state_bytes(gr.count));
+        if (gstate_bytes) CK(ctx->gstate.reserve(gstate_bytes));
+
+        for (const Group& gr : groups) {
+            {
+                StageScope sc(ctx, st, kStModel);
+                CK(launch_model_pass(ctx->sym.p, g, gr.s0, gr.count, ctx->queue.p, ctx->qoff.p, ctx->gstate.p, st));
+            }
+            {
+                StageScope sc(ctx, st, kStRange);
+                CK(launch_range_pass(ctx->queue.p, ctx->qoff.p, ctx->slice_bins.p, g, gr.s0, gr.count, ctx->scratch.p,
+                                     ctx->slice_bytes.p, ctx->d_status, st));
+            }
         }
     }
     {

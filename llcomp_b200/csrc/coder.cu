@@ -48,6 +48,106 @@ struct ModelShape {
     static constexpr int kSmem = kRowBytes + 256 * 4;
 };
 
+// Where the model pass puts its 16-bit entries: the bin queue in HBM (split kernels) or a shared-memory FIFO
+// (fused kernel).  `pos` counts from the first decision of the current 32-sample step.
+struct QueueSink {
+    uint16_t* q;
+    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { q[pos] = (uint16_t)w; }
+};
+constexpr int kFifo = 2048;                                  // entries; a multiple of the 256-decision block
+struct FifoSink {
+    uint16_t* fifo;
+    uint32_t base;
+    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { fifo[(base + pos) & (kFifo - 1)] = (uint16_t)w; }
+};
+
+// One step of the model pass: 32 consecutive samples, one per lane (rec = packed record of this lane's sample).
+// Returns the number of decisions the step produced.  llcomp.hpp:166-206 (binarisation), :440-443 (state).
+template <int K, class Sink>
+__device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint32_t cls, uint2* state,
+                                                const uint32_t* tab2, int lane, Sink sink) {
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t hash = rec >> 11;
+    const int d = ((int)(rec << 21)) >> 21;
+    const uint32_t a = (uint32_t)abs(d);
+    const int e = a ? 31 - __clz(a) : -1;                                 // -1 marks a zero residual
+    const uint32_t nb = valid ? 2u * e + 3u : 0u;                         // 1 decision for zero, else 2e+3
+
+    // exclusive scan of the decision counts (<= 19, five bit planes, no dependent shuffles)
+    uint32_t off = 0, total = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const uint32_t m = __ballot_sync(kFull, (nb >> b) & 1u);
+        off += __popc(m & lt_mask) << b;
+        total += __popc(m) << b;
+    }
+
+    // lanes of this class with the same context form a chain; its first lane carries the row through the members
+    const bool mine = valid && (hash % K) == cls;
+    const uint32_t key = mine ? hash : (0x10000u | lane);
+    uint32_t members = __match_any_sync(kFull, key);
+    const bool leader = mine && (__ffs(members) - 1 == lane);
+    const int rounds = __reduce_max_sync(kFull, mine ? __popc(members) : 0);
+    uint2 row = make_uint2(0, 0);
+    if (leader) row = state[hash / K];
+    uint32_t s0b = row.x & 0xFFu, s1b = (row.x >> 8) & 0xFFu, s2b = (row.x >> 16) & 0xFFu, s3b = row.x >> 24;
+    uint32_t s4b = row.y & 0xFFu, s5b = (row.y >> 8) & 0xFFu, s6b = (row.y >> 16) & 0xFFu, s7b = row.y >> 24;
+
+    for (int r = 0; r < rounds; ++r) {
+        const bool has = leader && members != 0;
+        const int src = has ? __ffs(members) - 1 : lane;
+        members &= members - 1;
+        const int md = __shfl_sync(kFull, d, src);
+        const uint32_t mo = __shfl_sync(kFull, off, src);
+        const uint32_t ma = (uint32_t)abs(md);
+        const int me = ma ? 31 - __clz(ma) : -1;
+        const int maxe = __reduce_max_sync(kFull, has ? me : -1);
+
+        // the sub-states are independent of one another: issue every look-up of the straight part first
+        const uint32_t w0 = tab2[s0b * 2 + (me < 0)];                                   // ctx 0, :187 / :204
+        const uint32_t w1 = tab2[s1b * 2 + (me >= 1)];                                  // ctx 1..3, :190-193
+        const uint32_t w2 = tab2[s2b * 2 + (me >= 2)];
+        const uint32_t w3 = tab2[s3b * 2 + (me >= 3)];
+        const uint32_t w5 = tab2[s5b * 2 + ((ma >> max(me - 1, 0)) & 1u)];             // ctx 5, first mantissa bit
+        const uint32_t w7 = tab2[s7b * 2 + (md < 0)];                                   // ctx 7, sign, :200-202
+        if (has) { sink.put(mo, w0); s0b = w0 >> 16; }
+        if (maxe >= 0) {
+            if (has && me >= 0) {
+                sink.put(mo + 1, w1); s1b = w1 >> 16;
+                sink.put(mo + 2 * me + 2, w7); s7b = w7 >> 16;
+            }
+            if (has && me >= 1) {
+                sink.put(mo + 2, w2); s2b = w2 >> 16;
+                sink.put(mo + me + 2, w5); s5b = w5 >> 16;
+            }
+            if (has && me >= 2) { sink.put(mo + 3, w3); s3b = w3 >> 16; }
+            for (int j = 0; j <= maxe - 3; ++j) {                                       // ctx 4: positions 4..e+1
+                const uint32_t w4 = tab2[s4b * 2 + (j < me - 3)];
+                if (has && j <= me - 3) { sink.put(mo + 4 + j, w4); s4b = w4 >> 16; }
+            }
+            for (int j = 0; j <= maxe - 2; ++j) {                                       // ctx 6: mantissa bits e-2..0
+                const uint32_t w6 = tab2[s6b * 2 + ((ma >> max(me - 2 - j, 0)) & 1u)];
+                if (has && j <= me - 2) { sink.put(mo + me + 3 + j, w6); s6b = w6 >> 16; }
+            }
+        }
+    }
+    if (leader)
+        state[hash / K] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
+                                     s4b | (s5b << 8) | (s6b << 16) | (s7b << 24));
+    __syncwarp();
+    return total;
+}
+
+// Table of the model pass: [state*2 + bit] = queue entry | next_state << 16 (llcomp.hpp:252-281, :290-292).
+__device__ __forceinline__ void fill_tab2(uint32_t* tab2, int lane) {
+    for (int i = lane; i < 256; i += 32) {
+        const uint32_t st = i >> 1, b = i & 1, e = c_tables.entry[st];
+        const uint32_t p = e & 0xFFu;
+        const uint32_t ns = (b == (st & 1u)) ? (e >> 8) & 0xFFu : (e >> 16) & 0xFFu;
+        tab2[i] = (b ? p : (256u - p) | 0x8000u) | (ns << 16);
+    }
+}
+
 // kGlobalState (K == 1): the rows live in global memory, pre-zeroed by the host, and are reached through L1
 // (116 vs 97 cycles per dependent read-modify-write, profiles/microbench/l1_rmw.cu); without 63 KB of shared
 // memory per slice every slice of a 1024-image batch is resident at once.
@@ -63,7 +163,6 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
     uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kRowBytes);       // [state*2 + bit] = entry | next << 16
 
     const int lane = threadIdx.x;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t cls = blockIdx.x % K;
     const uint64_t s = s0 + blockIdx.x / K;
     const Slice sl = slice_of(g, s);
@@ -72,12 +171,7 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
     uint16_t* q = queue + q_off[s];
 
     for (int i = lane; i < kRowBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = lane; i < 256; i += 32) {
-        const uint32_t st = i >> 1, b = i & 1, e = c_tables.entry[st];
-        const uint32_t p = e & 0xFFu;
-        const uint32_t ns = (b == (st & 1u)) ? (e >> 8) & 0xFFu : (e >> 16) & 0xFFu;   // llcomp.hpp:290-292
-        tab2[i] = (b ? p : (256u - p) | 0x8000u) | (ns << 16);
-    }
+    fill_tab2(tab2, lane);
     __syncwarp();
 
     uint32_t rec_next = lane < n ? in[lane] : 0u;
@@ -88,76 +182,7 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
             const uint64_t k = base + 32 + lane;
             rec_next = k < n ? in[k] : 0u;                                // next step's record flies under this step
         }
-        const uint32_t hash = rec >> 11;
-        const int d = ((int)(rec << 21)) >> 21;
-        const uint32_t a = (uint32_t)abs(d);
-        const int e = a ? 31 - __clz(a) : -1;                             // -1 marks a zero residual
-        const uint32_t nb = valid ? 2u * e + 3u : 0u;                     // 1 decision for zero, else 2e+3
-
-        // exclusive scan of the decision counts (<= 19, five bit planes, no dependent shuffles)
-        uint32_t off = 0, total = 0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) {
-            const uint32_t m = __ballot_sync(kFull, (nb >> b) & 1u);
-            off += __popc(m & lt_mask) << b;
-            total += __popc(m) << b;
-        }
-
-        // lanes of this class with the same context form a chain; its first lane carries the row through the members
-        const bool mine = valid && (hash % K) == cls;
-        const uint32_t key = mine ? hash : (0x10000u | lane);
-        uint32_t members = __match_any_sync(kFull, key);
-        const bool leader = mine && (__ffs(members) - 1 == lane);
-        const int rounds = __reduce_max_sync(kFull, mine ? __popc(members) : 0);
-        uint2 row = make_uint2(0, 0);
-        if (leader) row = state[hash / K];
-        uint32_t s0b = row.x & 0xFFu, s1b = (row.x >> 8) & 0xFFu, s2b = (row.x >> 16) & 0xFFu, s3b = row.x >> 24;
-        uint32_t s4b = row.y & 0xFFu, s5b = (row.y >> 8) & 0xFFu, s6b = (row.y >> 16) & 0xFFu, s7b = row.y >> 24;
-
-        for (int r = 0; r < rounds; ++r) {
-            const bool has = leader && members != 0;
-            const int src = has ? __ffs(members) - 1 : lane;
-            members &= members - 1;
-            const int md = __shfl_sync(kFull, d, src);
-            const uint32_t mo = __shfl_sync(kFull, off, src);
-            const uint32_t ma = (uint32_t)abs(md);
-            const int me = ma ? 31 - __clz(ma) : -1;
-            const int maxe = __reduce_max_sync(kFull, has ? me : -1);
-            uint16_t* qs = q + mo;
-
-            // the sub-states are independent of one another: issue every look-up of the straight part first
-            const uint32_t w0 = tab2[s0b * 2 + (me < 0)];                                   // ctx 0, :187 / :204
-            const uint32_t w1 = tab2[s1b * 2 + (me >= 1)];                                  // ctx 1..3, :190-193
-            const uint32_t w2 = tab2[s2b * 2 + (me >= 2)];
-            const uint32_t w3 = tab2[s3b * 2 + (me >= 3)];
-            const uint32_t w5 = tab2[s5b * 2 + ((ma >> max(me - 1, 0)) & 1u)];             // ctx 5, first mantissa bit
-            const uint32_t w7 = tab2[s7b * 2 + (md < 0)];                                   // ctx 7, sign, :200-202
-            if (has) { qs[0] = (uint16_t)w0; s0b = w0 >> 16; }
-            if (maxe >= 0) {
-                if (has && me >= 0) {
-                    qs[1] = (uint16_t)w1; s1b = w1 >> 16;
-                    qs[2 * me + 2] = (uint16_t)w7; s7b = w7 >> 16;
-                }
-                if (has && me >= 1) {
-                    qs[2] = (uint16_t)w2; s2b = w2 >> 16;
-                    qs[me + 2] = (uint16_t)w5; s5b = w5 >> 16;
-                }
-                if (has && me >= 2) { qs[3] = (uint16_t)w3; s3b = w3 >> 16; }
-                for (int j = 0; j <= maxe - 3; ++j) {                                       // ctx 4: positions 4..e+1
-                    const uint32_t w4 = tab2[s4b * 2 + (j < me - 3)];
-                    if (has && j <= me - 3) { qs[4 + j] = (uint16_t)w4; s4b = w4 >> 16; }
-                }
-                for (int j = 0; j <= maxe - 2; ++j) {                                       // ctx 6: mantissa bits e-2..0
-                    const uint32_t w6 = tab2[s6b * 2 + ((ma >> max(me - 2 - j, 0)) & 1u)];
-                    if (has && j <= me - 2) { qs[me + 3 + j] = (uint16_t)w6; s6b = w6 >> 16; }
-                }
-            }
-        }
-        if (leader)
-            state[hash / K] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
-                                     s4b | (s5b << 8) | (s6b << 16) | (s7b << 24));
-        __syncwarp();
-        q += total;
+        q += model_chunk<K>(rec, valid, cls, state, tab2, lane, QueueSink{q});
     }
 }
 
@@ -362,6 +387,80 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
     }
 }
 
+constexpr int kBlk = 256;                                    // decisions per block of the warp-specialised passes
+
+// Byte side of one block of `cnt` decisions (helper warp, lane-parallel over 32 decisions at a time): x values
+// from the chain, A operands (0 <=> the decision is a 1) from the operand ring.  Exact re-statement of the
+// low/carry half of RangeEncoder::put + renorm_encoder (llcomp.hpp:38-73).
+__device__ __forceinline__ void byte_side_block(ByteTail& t, bool& overflow, uint32_t& x_carry, const uint32_t* xr,
+                                                const uint2* inr, uint32_t cnt, int lane, uint8_t* out0,
+                                                uint8_t* out_end) {
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const bool live = base + lane < cnt;
+        const uint32_t x = live ? xr[base + lane] : 0x01000000u;      // inert: no renorm, delta 0
+        const uint32_t a = live ? inr[base + lane].y : 255u;
+        uint32_t xp = __shfl_up_sync(kFull, x, 1);
+        if (lane == 0) xp = x_carry;
+        x_carry = __shfl_sync(kFull, x, 31);
+        const bool any_dead = __any_sync(kFull, !live);
+        if (any_dead) {                          // keep the carry at the last live decision
+            const uint32_t last = cnt - base - 1;
+            x_carry = __shfl_sync(kFull, x, last);
+        }
+        const uint32_t r_before = xp < 0x10000u ? (xp & 0xFFFFFF00u) : (xp >> 8);
+        const uint32_t delta = (live && a == 0) ? r_before - (x >> 8) : 0u;
+        const uint32_t F = __ballot_sync(kFull, live && x < 0x10000u);   // renormalising decisions
+        uint32_t pre = delta;                    // inclusive prefix sum of the low increments
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, pre, d);
+            if (lane >= d) pre += y;
+        }
+        const uint32_t total = __shfl_sync(kFull, pre, 31);
+        if (F == 0) { t.low += total; continue; }
+        // segment sums: segment of lane i starts after the last renormalisation below i
+        const uint32_t below = F & ((1u << lane) - 1u);
+        const int p = below ? 31 - __clz(below) : -1;           // previous renormalising lane
+        const uint32_t pre_p = __shfl_sync(kFull, pre, p < 0 ? 0 : p);
+        const uint32_t seg = pre - (p < 0 ? 0u : pre_p);         // S_j when lane renormalises
+        const int first = __ffs(F) - 1;
+        // low at this lane's renormalisation (valid on lanes of F)
+        const uint32_t seg_p = __shfl_sync(kFull, seg, p < 0 ? 0 : p);
+        const uint32_t low_first_part = t.low;                   // low entering the sub-block
+        uint32_t low_ev;
+        if (p < 0) low_ev = low_first_part + seg;
+        else low_ev = (((seg_p + (p == first ? low_first_part : 0u)) & 0xFFu) << 8) + seg;
+        // feed the renormalisations through the byte/carry machine (llcomp.hpp:40-55)
+        if (t.outp + (t.hp >> 9) + 32 + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
+        const bool is_ev = (F >> lane) & 1u;
+        const int last_lane = 31 - __clz(F);
+        // Plain regime: a byte is latched, nothing is deferred, and no renormalisation of this sub-block
+        // defers one (low in 0xFF01..0xFFFF).  Then renormalisation j emits the byte latched by j-1 plus
+        // its own carry, independently of all the others: every lane writes its own byte.
+        const bool defers = is_ev && (low_ev - 0xFF01u) < 0xFFu;
+        if (t.hp < kHpEmpty && !__any_sync(kFull, defers)) {
+            const uint32_t low_p = __shfl_sync(kFull, low_ev, p < 0 ? 0 : p);
+            const uint32_t held = p < 0 ? t.hp : (low_p >> 8) & 0xFFu;
+            if (is_ev) t.outp[__popc(below)] = (uint8_t)(held + (low_ev >> 16));
+            const uint32_t low_last = __shfl_sync(kFull, low_ev, last_lane);
+            t.outp += __popc(F);
+            t.hp = (low_last >> 8) & 0xFFu;
+            t.low = (low_last & 0xFFu) << 8;
+        } else {
+            uint32_t todo = F;
+            do {
+                const int i = __ffs(todo) - 1;
+                todo &= todo - 1;
+                t.low = __shfl_sync(kFull, low_ev, i);
+                shift_low(t);
+            } while (todo);
+        }
+        // decisions after the last renormalisation of the sub-block
+        const uint32_t pre_last = __shfl_sync(kFull, pre, last_lane);
+        t.low += total - pre_last;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K2b, warp-specialised form (one CTA of two warps per slice).
 //   chain warp   only the range recurrence x = range*M + A; range' = x < 0x10000 ? x & ~0xFF : x >> 8, four
@@ -374,7 +473,6 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t*
 //                and feeds those through the byte/carry machine of renorm_encoder (llcomp.hpp:38-58).
 // One __syncthreads per 256-decision block; both rings are double buffered.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kBlk = 256;                                    // decisions per block
 
 __device__ __forceinline__ void pair_sync() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
@@ -457,72 +555,7 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
             if (b > 0 && debug_skip != 2) {                  // byte side of block b-1
                 const uint32_t pb = b - 1;
                 const uint32_t cnt = (uint32_t)min((uint64_t)kBlk, nb - (uint64_t)pb * kBlk);
-                const uint32_t* xr = x_ring[pb & 1];
-                const uint2* inr = in_ring[pb & 1];
-                for (uint32_t base = 0; base < cnt; base += 32) {
-                    const bool live = base + lane < cnt;
-                    const uint32_t x = live ? xr[base + lane] : 0x01000000u;      // inert: no renorm, delta 0
-                    const uint32_t a = live ? inr[base + lane].y : 255u;
-                    uint32_t xp = __shfl_up_sync(kFull, x, 1);
-                    if (lane == 0) xp = x_carry;
-                    x_carry = __shfl_sync(kFull, x, 31);
-                    const bool any_dead = __any_sync(kFull, !live);
-                    if (any_dead) {                          // keep the carry at the last live decision
-                        const uint32_t last = cnt - base - 1;
-                        x_carry = __shfl_sync(kFull, x, last);
-                    }
-                    const uint32_t r_before = xp < 0x10000u ? (xp & 0xFFFFFF00u) : (xp >> 8);
-                    const uint32_t delta = (live && a == 0) ? r_before - (x >> 8) : 0u;
-                    const uint32_t F = __ballot_sync(kFull, live && x < 0x10000u);   // renormalising decisions
-                    uint32_t pre = delta;                    // inclusive prefix sum of the low increments
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t y = __shfl_up_sync(kFull, pre, d);
-                        if (lane >= d) pre += y;
-                    }
-                    const uint32_t total = __shfl_sync(kFull, pre, 31);
-                    if (F == 0) { t.low += total; continue; }
-                    // segment sums: segment of lane i starts after the last renormalisation below i
-                    const uint32_t below = F & ((1u << lane) - 1u);
-                    const int p = below ? 31 - __clz(below) : -1;           // previous renormalising lane
-                    const uint32_t pre_p = __shfl_sync(kFull, pre, p < 0 ? 0 : p);
-                    const uint32_t seg = pre - (p < 0 ? 0u : pre_p);         // S_j when lane renormalises
-                    const int first = __ffs(F) - 1;
-                    // low at this lane's renormalisation (valid on lanes of F)
-                    const uint32_t seg_p = __shfl_sync(kFull, seg, p < 0 ? 0 : p);
-                    const uint32_t low_first_part = t.low;                   // low entering the sub-block
-                    uint32_t low_ev;
-                    if (p < 0) low_ev = low_first_part + seg;
-                    else low_ev = (((seg_p + (p == first ? low_first_part : 0u)) & 0xFFu) << 8) + seg;
-                    // feed the renormalisations through the byte/carry machine (llcomp.hpp:40-55)
-                    if (t.outp + (t.hp >> 9) + 32 + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
-                    const bool is_ev = (F >> lane) & 1u;
-                    const int last_lane = 31 - __clz(F);
-                    // Plain regime: a byte is latched, nothing is deferred, and no renormalisation of this sub-block
-                    // defers one (low in 0xFF01..0xFFFF).  Then renormalisation j emits the byte latched by j-1 plus
-                    // its own carry, independently of all the others: every lane writes its own byte.
-                    const bool defers = is_ev && (low_ev - 0xFF01u) < 0xFFu;
-                    if (t.hp < kHpEmpty && !__any_sync(kFull, defers)) {
-                        const uint32_t low_p = __shfl_sync(kFull, low_ev, p < 0 ? 0 : p);
-                        const uint32_t held = p < 0 ? t.hp : (low_p >> 8) & 0xFFu;
-                        if (is_ev) t.outp[__popc(below)] = (uint8_t)(held + (low_ev >> 16));
-                        const uint32_t low_last = __shfl_sync(kFull, low_ev, last_lane);
-                        t.outp += __popc(F);
-                        t.hp = (low_last >> 8) & 0xFFu;
-                        t.low = (low_last & 0xFFu) << 8;
-                    } else {
-                        uint32_t todo = F;
-                        do {
-                            const int i = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            t.low = __shfl_sync(kFull, low_ev, i);
-                            shift_low(t);
-                        } while (todo);
-                    }
-                    // decisions after the last renormalisation of the sub-block
-                    const uint32_t pre_last = __shfl_sync(kFull, pre, last_lane);
-                    t.low += total - pre_last;
-                }
+                byte_side_block(t, overflow, x_carry, x_ring[pb & 1], in_ring[pb & 1], cnt, lane, out0, out_end);
             }
             if (b + 1 < n_blk) {                             // operands of block b+1, entries of block b+2
                 expand(e_next, (b + 1) & 1);
@@ -546,9 +579,178 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2 fused: records -> slice payload in ONE kernel, three warps per slice, no bin queue in HBM.
+//   model warp   the model pass above, its entries go to a shared-memory FIFO instead of HBM;
+//   chain warp   the range recurrence (4 instructions per decision), as in k_range_pass_ws;
+//   helper warp  expands FIFO entries to (M, A) operands for the chain and runs the lane-parallel byte side.
+// The three meet at one named barrier per 256-decision block.  Before the barrier that ends iteration i the
+// model warp has produced at least (i+3) blocks (or everything); in iteration b the helper expands block b+1,
+// the chain runs block b, the helper turns block b-1 into bytes.  With the state rows behind L1 (kGlobalState)
+// the CTA needs ~12 KB of shared memory, so every slice of a 1024-image batch is resident; with the rows in
+// shared memory (<= 3 slices per SM) it takes 75 KB.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void trio_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+
+template <bool kGlobalState>
+__global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __restrict__ sym, Geom g,
+                                                          uint8_t* __restrict__ scratch,
+                                                          uint32_t* __restrict__ slice_bytes, int* __restrict__ status,
+                                                          uint2* __restrict__ gstate) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kRowBytes = kGlobalState ? 0 : ModelShape<1>::kRowBytes;
+    uint2* state = kGlobalState ? gstate + (size_t)blockIdx.x * kContexts : reinterpret_cast<uint2*>(smem);
+    uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kRowBytes);
+    uint16_t* fifo = reinterpret_cast<uint16_t*>(smem + kRowBytes + 1024);
+    uint2 (*in_ring)[kBlk + 4] = reinterpret_cast<uint2 (*)[kBlk + 4]>(smem + kRowBytes + 1024 + kFifo * 2);
+    uint32_t (*x_ring)[kBlk] = reinterpret_cast<uint32_t (*)[kBlk]>(smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlk + 4) * 8);
+    volatile unsigned long long* ctl = reinterpret_cast<volatile unsigned long long*>(
+        smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlk + 4) * 8 + 2 * kBlk * 4);
+    // Control words, double buffered by iteration parity p: ctl[2p] = decisions produced so far,
+    // ctl[2p+1] = 1 once the model warp has seen every sample.  Written by the model warp before the barrier
+    // that opens iteration p, read by everybody right after it.
+
+    // Four warp slots, three used; the assignment rotates with the CTA index to spread the chain warps of the
+    // CTAs that share an SM over its four schedulers.
+    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+    const int r0 = blockIdx.x & 3;
+    const int role = (wslot - r0) & 3;                       // 0 chain, 1 model, 2 helper, 3 unused
+    if (role == 3) return;
+
+    const uint64_t s = blockIdx.x;
+    const Slice sl = slice_of(g, s);
+    const uint32_t* in = sym + sl.sym_off;
+    const uint64_t n = sl.n;
+
+    if (role == 1) {
+        if (!kGlobalState)
+            for (int i = lane; i < kRowBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+        fill_tab2(tab2, lane);
+        __syncwarp();
+    }
+
+    // ---- model warp state
+    uint64_t base = 0;
+    uint64_t produced = 0;                                   // decisions so far
+    uint32_t rec_next = (role == 1 && lane < n) ? in[lane] : 0u;
+    // model warp: run steps until `target` decisions exist, then publish the counters for iteration `for_iter`
+    auto produce_until = [&](uint64_t target, uint32_t for_iter) {
+        while (base < n && produced < target) {
+            const uint32_t rec = rec_next;
+            const bool valid = base + lane < n;
+            const uint64_t k = base + 32 + lane;
+            rec_next = k < n ? in[k] : 0u;
+            produced += model_chunk<1>(rec, valid, 0u, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
+            base += 32;
+        }
+        if (lane == 0) { ctl[2 * (for_iter & 1)] = produced; ctl[2 * (for_iter & 1) + 1] = base >= n ? 1ull : 0ull; }
+        __syncwarp();
+    };
+    // ---- helper warp state
+    uint8_t* const out0 = scratch + scratch_off(sl, s);
+    uint8_t* const out_end = out0 + scratch_cap(sl);
+    ByteTail t;
+    t.low = 0; t.hp = kHpEmpty; t.outp = out0;               // llcomp.hpp:35
+    bool overflow = false;
+    uint32_t x_carry = 0xFF00u << 8;                         // pseudo-x whose successor range is the initial 0xFF00
+    // ---- chain warp state
+    uint32_t range = 0xFF00u;
+
+    auto expand = [&](uint32_t blk) {                        // helper: FIFO entries of block blk -> (M, A) operands
+        const uint4 e = *reinterpret_cast<const uint4*>(fifo + ((blk * kBlk) & (kFifo - 1)) + lane * 8);
+        const uint32_t w[4] = {e.x, e.y, e.z, e.w};
+        uint4* dst = reinterpret_cast<uint4*>(&in_ring[blk & 1][lane * 8]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            dst[k] = make_uint4(w[k] & 0xFFu, prmt(w[k], 0x4449), prmt(w[k], 0x4442), prmt(w[k], 0x444B));
+    };
+
+    // prime: three blocks of decisions, block 0 expanded
+    if (role == 1) produce_until(3 * kBlk, 0);
+    trio_sync();
+    if (role == 2) expand(0);
+    trio_sync();
+
+    for (uint32_t b = 0;; ++b) {
+        // every warp reads the same control words here (written before the barrier that just completed)
+        const unsigned long long prod = ctl[2 * (b & 1)];
+        const bool fin = ctl[2 * (b & 1) + 1] != 0;
+        // number of decisions of block k known to exist: 256 unless finished and it is the last, partial one
+        auto block_count = [&](uint32_t k) -> int {          // <= 0: the block does not exist
+            if (!fin) return kBlk;
+            const long long left = (long long)prod - (long long)k * kBlk;
+            return left > kBlk ? kBlk : (int)left;
+        };
+        const int cnt_prev = b > 0 ? block_count(b - 1) : 0;
+        const int cnt_cur = block_count(b);
+        const int cnt_next = block_count(b + 1);
+        if (cnt_cur <= 0 && cnt_prev <= 0) break;            // nothing left for anybody
+
+        if (role == 0) {
+            if (cnt_cur > 0) {
+                const uint4* inp = reinterpret_cast<const uint4*>(in_ring[b & 1]);
+                uint4* xo = reinterpret_cast<uint4*>(x_ring[b & 1]);
+                const uint32_t n4 = ((uint32_t)cnt_cur + 3) / 4;      // garbage beyond cnt is computed and ignored
+                uint4 p0 = inp[0], p1 = inp[1];
+#pragma unroll 4
+                for (uint32_t v = n4; v > 0; --v) {
+                    inp += 2;
+                    const uint4 q0 = inp[0], q1 = inp[1];
+                    uint4 xs;
+                    xs.x = range * p0.x + p0.y; range = xs.x < 0x10000u ? (xs.x & 0xFFFFFF00u) : (xs.x >> 8);
+                    xs.y = range * p0.z + p0.w; range = xs.y < 0x10000u ? (xs.y & 0xFFFFFF00u) : (xs.y >> 8);
+                    xs.z = range * p1.x + p1.y; range = xs.z < 0x10000u ? (xs.z & 0xFFFFFF00u) : (xs.z >> 8);
+                    xs.w = range * p1.z + p1.w; range = xs.w < 0x10000u ? (xs.w & 0xFFFFFF00u) : (xs.w >> 8);
+                    *xo++ = xs;
+                    p0 = q0; p1 = q1;
+                }
+            }
+        } else if (role == 1) {
+            produce_until((uint64_t)(b + 4) * kBlk, b + 1);
+        } else {
+            if (cnt_prev > 0) byte_side_block(t, overflow, x_carry, x_ring[(b - 1) & 1], in_ring[(b - 1) & 1],
+                                              (uint32_t)cnt_prev, lane, out0, out_end);
+            if (cnt_next > 0) expand(b + 1);
+        }
+        trio_sync();
+    }
+
+    if (role == 2) {
+        if (t.outp + (t.hp >> 9) + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
+        // finish(), llcomp.hpp:75-81: range = 0xFF both times, so each renorm_encoder call shifts exactly once
+        t.low += 0xFFu;
+        shift_low(t);
+        shift_low(t);
+        if (lane == 0) {
+            slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(t.outp - out0);
+            if (overflow) atomicCAS(status, kDevOk, kDevOverflow);
+        }
+    }
+}
+
+constexpr int kFusedSmemNoState = 1024 + kFifo * 2 + 2 * (kBlk + 4) * 8 + 2 * kBlk * 4 + 32;
+
+cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
+                                     int* d_status, uint8_t* d_gstate, cudaStream_t st) {
+    const uint64_t ns = g.n_slices();
+    if (ns == 0 || ns > 0x0FFFFFFFull) return cudaErrorInvalidValue;
+    if (model_global_state_bytes(ns)) {
+        cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);      // all states start at 0
+        if (e != cudaSuccess) return e;
+        k_slice_coder_fused<true><<<(unsigned)ns, 128, kFusedSmemNoState, st>>>(d_sym, g, d_scratch, d_slice_bytes,
+                                                                                 d_status, reinterpret_cast<uint2*>(d_gstate));
+    } else {
+        k_slice_coder_fused<false><<<(unsigned)ns, 128, kFusedSmemNoState + ModelShape<1>::kRowBytes, st>>>(
+            d_sym, g, d_scratch, d_slice_bytes, d_status, nullptr);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 cudaError_t configure_slice_coder() {
     cudaError_t e = cudaFuncSetAttribute(k_model_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<1>::kSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_model_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<2>::kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   kFusedSmemNoState + ModelShape<1>::kRowBytes);
     return e;
 }
 

@@ -242,18 +242,24 @@ def test_batch_streams_are_standalone_reference_streams(codec):
     assert int(off2[-1]) > int(off[-1])
 
 
-def test_small_queue_budget_forces_launch_groups(codec):
+def test_split_coder_path_and_launch_groups(codec):
+    """The two-kernel coder (model pass -> bin queue in HBM -> range pass) stays available behind
+    LLCOMP_CODER_SPLIT; a small queue budget forces it to code the slices in several launch groups."""
     import torch
     imgs = np.stack([oracle.generate(128, 96, 3, 8, 70 + k) for k in range(7)])
     g = codec.geometry(128, 96, 3, 64, 48, 7)
     d_px = torch.from_numpy(imgs).cuda()
-    ref_payload, ref_off = codec.encode_device(d_px, g)
+    ref_payload, ref_off = codec.encode_device(d_px, g)          # default: fused coder
     codec.finish()
+    os.environ["LLCOMP_CODER_SPLIT"] = "1"
     codec.set_queue_budget(200_000)                 # ~3 slices per group instead of all 28
     try:
         payload, off = codec.encode_device(d_px, g)
         codec.finish()
+        assert codec.last_bin_count() == sum(oracle.count_bins(imgs[k][y0:y0 + 48, x0:x0 + 64]) for k in range(7)
+                                             for (x0, y0, _, _) in tiles_of(128, 96, 64, 48))
     finally:
+        del os.environ["LLCOMP_CODER_SPLIT"]
         codec.set_queue_budget(64 << 30)
     assert torch.equal(off, ref_off)
     n = int(off[-1])
@@ -274,12 +280,17 @@ def test_many_slices_decode_with_state_behind_l1(codec):
     codec.finish()
     assert torch.equal(out.view(16, 192, 256, 3), d_px)
     os.environ["LLCOMP_DECODER_SMEM_STATE"] = "1"                     # same answer with the state in shared memory
+    os.environ["LLCOMP_CODER_SPLIT"] = "1"                            # ... and from the two-kernel coder
     try:
         out2 = codec.decode_device(payload, offsets, g)
         codec.finish()
+        payload2, offsets2 = codec.encode_device(d_px, g)
+        codec.finish()
     finally:
         del os.environ["LLCOMP_DECODER_SMEM_STATE"]
+        del os.environ["LLCOMP_CODER_SPLIT"]
     assert torch.equal(out2, out)
+    assert torch.equal(offsets2, offsets) and torch.equal(payload2[: int(offsets[-1])], payload[: int(offsets[-1])])
     off = offsets.cpu().numpy()
     k = 48 * 5 + 17                                                   # one slice against the oracle
     x0, y0, sw, sh = tiles_of(256, 192, 32, 32)[17]
