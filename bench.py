@@ -86,6 +86,9 @@ def synth_batch(torch, n, w, h, c, noise, seed, device):
     step = max(1, min(n, 64))
     for i in range(0, n, step):
         m = min(step, n - i)
+        if noise < 0:                      # high-entropy variant: uniform random bytes (BASELINE configs[2])
+            out[i:i + m] = torch.randint(0, 256, (m, h, w, c), generator=g, device=device, dtype=torch.int32).to(torch.uint8)
+            continue
         v = (x + y) // 2 + ch
         if noise > 0:
             v = v + torch.randint(-noise, noise + 1, (m, h, w, c), generator=g, device=device, dtype=torch.int32)
@@ -149,8 +152,10 @@ def main():
     W = H = args.size
     C, n_img = args.channels, args.images
     cores = os.cpu_count() or 1
-    workload = (f"configs[3]: batch of {n_img} x {W}x{H} RGB{8 if C == 3 else ''} (C={C}) per GPU, gradient + "
-                f"uniform noise +-{args.noise}, " + ("1 slice per image" if not args.tile else f"{args.tile}^2 tiles"))
+    content = "uniform random bytes" if args.noise < 0 else f"gradient + uniform noise +-{args.noise}"
+    workload = (f"{'configs[3]: ' if (n_img, W, C, args.tile, args.noise) == (1024, 1024, 3, 0, 4) else ''}batch of {n_img} x {W}x{H} "
+                f"RGB{8 if C == 3 else ''} (C={C}) per GPU, {content}, "
+                + ("1 slice per image" if not args.tile else f"{args.tile}^2 tiles"))
     config = {"workload": workload, "images_per_gpu": n_img, "width": W, "height": H, "channels": C,
               "noise": args.noise, "tile": args.tile or None, "slices_per_gpu": None, "sharding": f"dp{world}",
               "l2": "inputs (>= 3 GB per step) are larger than the 126 MB L2"}
@@ -268,7 +273,7 @@ def main():
     if not args.no_e2e:
         h_px = torch.empty((n_img, H, W, C), dtype=torch.uint8, pin_memory=True)
         h_px.copy_(px)
-        out_cap = raw + 384 * n_img + hdr * n_img
+        out_cap = (raw if args.noise >= 0 else 2 * raw) + 384 * n_slices + hdr * n_img
         h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
         h_off = torch.zeros(n_img + 1, dtype=torch.int64, pin_memory=True)
         h_back = torch.empty((n_img, H, W, C), dtype=torch.uint8, pin_memory=True)

@@ -86,10 +86,21 @@ __device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint32
     const bool mine = valid && (hash % K) == cls;
     const uint32_t key = mine ? hash : (0x10000u | lane);
     uint32_t members = __match_any_sync(kFull, key);
-    const bool leader = mine && (__ffs(members) - 1 == lane);
-    const int rounds = __reduce_max_sync(kFull, mine ? __popc(members) : 0);
+    const int head = __ffs(members) - 1;
+    const bool leader = mine && head == lane;
     uint2 row = make_uint2(0, 0);
     if (leader) row = state[hash / K];
+    // Smooth content: every member of the chain has a zero residual (one decision, "is zero" = 1, sub-state 0) and
+    // that sub-state sits in the saturated state 127 (MPS 1, next-if-MPS 127, llcomp.hpp:258).  Then every member
+    // gets the same entry and the row does not change: no need to walk the chain member by member.
+    const uint32_t zero_mask = __ballot_sync(kFull, valid && a == 0);
+    const bool flat = leader && (members & ~zero_mask) == 0 && (row.x & 0xFFu) == 127u;
+    if (__any_sync(kFull, flat)) {
+        const bool flat_chain = __shfl_sync(kFull, flat, head);          // every lane takes part in the shuffle
+        if (mine && flat_chain) sink.put(off, tab2[127 * 2 + 1]);
+        if (flat) members = 0;
+    }
+    const int rounds = __reduce_max_sync(kFull, leader ? __popc(members) : 0);
     uint32_t s0b = row.x & 0xFFu, s1b = (row.x >> 8) & 0xFFu, s2b = (row.x >> 16) & 0xFFu, s3b = row.x >> 24;
     uint32_t s4b = row.y & 0xFFu, s5b = (row.y >> 8) & 0xFFu, s6b = (row.y >> 16) & 0xFFu, s7b = row.y >> 24;
 

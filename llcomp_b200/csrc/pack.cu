@@ -59,7 +59,7 @@ cudaError_t launch_scan(const uint32_t* d_slice_bytes, uint64_t n_slices, uint64
 }
 
 // ---- K4 ------------------------------------------------------------------------------------
-// grid = (parts, n_slices): CTA (p, s) copies a strided set of 4 KB pieces of slice s.  The destination is
+// grid = (n_slices, parts): CTA (s, p) copies a strided set of 4 KB pieces of slice s.  The destination is
 // written with 16-byte stores on 16-byte boundaries; the (arbitrarily aligned) source is read as aligned
 // 32-bit words and realigned with funnel shifts.
 constexpr int kCompactThreads = 256;
@@ -77,7 +77,7 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
 __global__ void __launch_bounds__(kCompactThreads) k_compact(const uint8_t* __restrict__ scratch, Geom g,
                                                              const uint64_t* __restrict__ offsets,
                                                              uint8_t* __restrict__ payload, uint64_t capacity) {
-    const uint64_t s = blockIdx.y;
+    const uint64_t s = blockIdx.x;
     const Slice sl = slice_of(g, s);
     const uint64_t o0 = offsets[s], o1 = offsets[s + 1];
     if (o1 > capacity) return;                               // overflow already flagged by the scan
@@ -89,15 +89,15 @@ __global__ void __launch_bounds__(kCompactThreads) k_compact(const uint8_t* __re
     // bytes up to the first 16-byte boundary of dst, then whole 16-byte units, then the tail
     const uint64_t head = min(len, (uint64_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
     const uint64_t body = (len - head) / 16;
-    if (blockIdx.x == 0) {
+    if (blockIdx.y == 0) {
         if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
         const uint64_t tail0 = head + body * 16;
         if (tail0 + threadIdx.x < len) dst[tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
     }
     const uint8_t* sb = src + head;
     uint4* db = reinterpret_cast<uint4*>(dst + head);
-    for (uint64_t u = (uint64_t)blockIdx.x * kCompactThreads + threadIdx.x; u < body;
-         u += (uint64_t)gridDim.x * kCompactThreads) {
+    for (uint64_t u = (uint64_t)blockIdx.y * kCompactThreads + threadIdx.x; u < body;
+         u += (uint64_t)gridDim.y * kCompactThreads) {
         const uint8_t* q = sb + u * 16;
         uint4 v;
         v.x = load_u32_unaligned(q);
@@ -111,14 +111,15 @@ __global__ void __launch_bounds__(kCompactThreads) k_compact(const uint8_t* __re
 cudaError_t launch_compact(const uint8_t* d_scratch, const Geom& g, const uint64_t* d_offsets, uint8_t* d_payload,
                            uint64_t capacity, cudaStream_t st) {
     const uint64_t ns = g.n_slices();
-    if (ns > 65535) return cudaErrorInvalidValue;            // TODO(next): fold large slice counts into x
+    if (ns > 0x7FFFFFFFull) return cudaErrorInvalidValue;
     // enough CTAs per slice to cover ~2x raw in 4 KB pieces, bounded so the grid stays near 8 CTAs/SM
     const uint64_t max_bytes = 2ull * (uint64_t)min(g.tw, g.W) * min(g.th, g.H) * g.C + kScratchSlack;
     uint64_t parts = (max_bytes + kPiece - 1) / kPiece;
     const uint64_t want = (148ull * 8 + ns - 1) / ns;
     if (parts > want) parts = want;
     if (parts < 1) parts = 1;
-    dim3 grid((unsigned)parts, (unsigned)ns);
+    if (parts > 65535) parts = 65535;
+    dim3 grid((unsigned)ns, (unsigned)parts);
     k_compact<<<grid, kCompactThreads, 0, st>>>(d_scratch, g, d_offsets, d_payload, capacity);
     return cudaGetLastError();
 }
