@@ -102,11 +102,13 @@ __global__ void __launch_bounds__(256) k_frontend_simple(const uint8_t* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
-// v2 mapping for 3- and 4-channel images: a CTA stages the post-transform planes of an image region
-// (kTileH x kTileW pixels plus a 2-row / 2+1-column halo) in shared memory ONCE, as one 8-byte pixel
-// (4 x int16), then every thread codes pixels of that region from shared memory.  Interior pixels of a
-// slice take a branch-free path with table-driven quantisers (premultiplied by their hash weights);
-// pixels on a slice border take the substitution chain of llcomp.hpp:417-422.
+// Tiled mapping for 3- and 4-channel images: a CTA stages the post-transform planes of an image region
+// (kTileH x kTileW pixels plus a 2-row / 2+1-column halo) in shared memory ONCE, as one 16-byte pixel
+// (4 x int32, so that a neighbour is one LDS.128 and needs no unpacking), then every thread codes pixels of
+// that region from shared memory.  Interior pixels of a slice take a branch-free path with table-driven
+// quantisers (premultiplied by their hash weights); pixels on a slice border take the substitution chain of
+// llcomp.hpp:417-422.  No integer division in the loops: the region meets at most one slice boundary per axis
+// when tiles are at least as large as the region (smaller tiles fall back to the simple kernel).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTileW = 64, kTileH = 16;
 constexpr int kHaloL = 2, kHaloR = 1, kHaloT = 2;
@@ -121,116 +123,115 @@ struct QuantLuts {
     int16_t d[256];   // q5(x) * 605         (L - l)
     int16_t e[256];   // q5(x) * 3025        (T - t)
 };
+constexpr QuantLuts make_quant_luts() {
+    QuantLuts t{};
+    for (int i = 0; i < 256; ++i) {
+        const int x = i - 128, a = x < 0 ? -x : x;
+        const int m11 = (a >= 1) + (a >= 2) + (a >= 5) + (a >= 12) + (a >= 35), m5 = (a >= 1) + (a >= 4);
+        const int q11 = x < 0 ? -m11 : m11, q5 = x < 0 ? -m5 : m5;
+        t.a[i] = (int16_t)q11; t.b[i] = (int16_t)(q11 * 11); t.c[i] = (int16_t)(q11 * 121);
+        t.d[i] = (int16_t)(q5 * 605); t.e[i] = (int16_t)(q5 * 3025);
+    }
+    return t;
+}
+__constant__ QuantLuts c_quant_luts = make_quant_luts();
 
-__device__ __forceinline__ int clamp8(int x) { return max(-128, min(127, x)); }
+__device__ __forceinline__ int lut_index(int x) { return max(0, min(255, x + 128)); }   // clamp to [-128,127], + 128
 
-template <int CT>
-__global__ void __launch_bounds__(256) k_frontend_tiled(const uint8_t* __restrict__ pixels, Geom g,
+template <int CT, bool kCount>
+__global__ void __launch_bounds__(256, 6) k_frontend_tiled(const uint8_t* __restrict__ pixels, Geom g,
                                                         uint32_t* __restrict__ sym,
                                                         unsigned long long* __restrict__ slice_bins) {
-    static_assert(CT == 3 || CT == 4, "8-byte staged pixels hold 3 or 4 planes");
-    __shared__ short4 tile[kSmemH][kSmemW];
-    __shared__ QuantLuts lut;
+    static_assert(CT == 3 || CT == 4, "staged pixels hold 3 or 4 planes");
+    __shared__ int4 tile[kSmemH][kSmemW];
+    __shared__ __align__(16) QuantLuts lut;
     __shared__ unsigned int cta_bins;                      // decisions of the region's first slice (<= 1024*4*19)
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.z;
     const int rx0 = blockIdx.x * kTileW, ry0 = blockIdx.y * kTileH;     // region origin in the image
     const size_t pitch = (size_t)g.W * CT;
     const uint8_t* base = pixels + (size_t)img * g.H * pitch;
 
-    if (tid == 0) cta_bins = 0;
-    for (int i = tid; i < 256; i += 256) {
-        const int x = i - 128;
-        const int q11 = quant11(x), q5 = quant5(x);
-        lut.a[i] = (int16_t)q11; lut.b[i] = (int16_t)(q11 * 11); lut.c[i] = (int16_t)(q11 * 121);
-        lut.d[i] = (int16_t)(q5 * 605); lut.e[i] = (int16_t)(q5 * 3025);
-    }
-    // stage the planes (llcomp.hpp:396-409); coordinates clamped to the image, clamped copies are never used
-    for (int i = tid; i < kSmemH * kSmemW; i += 256) {
-        const int sy = i / kSmemW, sx = i - sy * kSmemW;
+    if (kCount && tid == 0) cta_bins = 0;
+    if (tid < (int)(sizeof(QuantLuts) / 16))
+        reinterpret_cast<uint4*>(&lut)[tid] = reinterpret_cast<const uint4*>(&c_quant_luts)[tid];
+    // stage the planes (llcomp.hpp:396-409): warp w takes rows w, w+8, w+16; coordinates clamped to the image
+    // (clamped copies are never used as neighbours of a valid in-slice pixel)
+    for (int sy = warp; sy < kSmemH; sy += 8) {
         const int y = min(max(ry0 + sy - kHaloT, 0), g.H - 1);
-        const int x = min(max(rx0 + sx - kHaloL, 0), g.W - 1);
-        const uint8_t* p = base + (size_t)y * pitch + (size_t)x * CT;
-        const int gg = p[1];
-        const int r = (int)p[0] - gg, b = (int)p[2] - gg;
-        short4 v;
-        v.x = (short)r; v.y = (short)(gg + (b + r) / 4); v.z = (short)b; v.w = CT == 4 ? (short)p[3] : (short)0;
-        tile[sy][sx] = v;
+        const uint8_t* rowp = base + (size_t)y * pitch;
+        for (int sx = lane; sx < kSmemW; sx += 32) {
+            const int x = min(max(rx0 + sx - kHaloL, 0), g.W - 1);
+            const uint8_t* p = rowp + x * CT;
+            const int gg = p[1];
+            const int r = (int)p[0] - gg, b = (int)p[2] - gg;
+            tile[sy][sx] = make_int4(r, gg + (b + r) / 4, b, CT == 4 ? (int)p[3] : 0);
+        }
     }
     __syncthreads();
 
+    // slice geometry of this thread's column and of the (at most two) tile rows the region touches
     const int lx = tid & (kTileW - 1);                                  // column inside the region
     const int x = rx0 + lx;
     const int tx = min(x, g.W - 1) / g.tw;
     const int x0 = tx * g.tw;
     const int sw = min(g.tw, g.W - x0);
     const int w = x - x0;
-    // Decision counts: one global atomic per CTA for the slice of the region's first pixel (all of the region,
-    // unless a slice boundary crosses it); pixels of other slices add directly.
-    const unsigned primary = (unsigned)img * g.slices_per_image() + (ry0 / g.th) * g.tiles_x + rx0 / g.tw;
+    const int ty_a = ry0 / g.th;                                        // tile row of the region's first row
+    const int yb = (ty_a + 1) * g.th;                                   // first image row of the next tile row
+    const unsigned primary = (unsigned)img * g.slices_per_image() + ty_a * g.tiles_x + rx0 / g.tw;
+    uint32_t* const img_out = sym + (size_t)img * g.image_samples();
     unsigned acc = 0;
 #pragma unroll 1
     for (int ly = tid / kTileW; ly < kTileH; ly += 256 / kTileW) {
         const int y = ry0 + ly;
-        const bool valid = x < g.W && y < g.H;
-        const int ty = min(y, g.H - 1) / g.th;
-        const int y0 = ty * g.th;
+        if (x >= g.W || y >= g.H) continue;
+        const int ty = ty_a + (y >= yb);
+        const int y0 = y >= yb ? yb : ty_a * g.th;
         const int sh = min(g.th, g.H - y0);
         const int h = y - y0;
-        unsigned bins = 0;
-        if (valid) {
-            uint32_t* out = sym + (size_t)img * g.image_samples() + ((size_t)y0 * g.W + (size_t)x0 * sh) * CT +
-                            ((size_t)h * sw + w) * CT;
-            const int sy = ly + kHaloT, sx = lx + kHaloL;
-            const short4 pc = tile[sy][sx];
-            const int cur[4] = {pc.x, pc.y, pc.z, pc.w};
-            int l[4], t[4], L[4], tl[4], tr[4], T[4];
-            if (w >= 2 && w < sw - 1 && h >= 2) {                       // interior of the slice
-                const short4 pl = tile[sy][sx - 1], pL = tile[sy][sx - 2];
-                const short4 ptl = tile[sy - 1][sx - 1], pt = tile[sy - 1][sx], ptr = tile[sy - 1][sx + 1];
-                const short4 pT = tile[sy - 2][sx];
-                l[0] = pl.x; l[1] = pl.y; l[2] = pl.z; l[3] = pl.w;
-                L[0] = pL.x; L[1] = pL.y; L[2] = pL.z; L[3] = pL.w;
-                tl[0] = ptl.x; tl[1] = ptl.y; tl[2] = ptl.z; tl[3] = ptl.w;
-                t[0] = pt.x; t[1] = pt.y; t[2] = pt.z; t[3] = pt.w;
-                tr[0] = ptr.x; tr[1] = ptr.y; tr[2] = ptr.z; tr[3] = ptr.w;
-                T[0] = pT.x; T[1] = pT.y; T[2] = pT.z; T[3] = pT.w;
-            } else {                                                    // llcomp.hpp:417-422
-#pragma unroll
-                for (int i = 0; i < CT; ++i) {
-                    auto P = [&](int dy, int dx) {
-                        const short4 q = tile[sy + dy][sx + dx];
-                        return i == 0 ? (int)q.x : i == 1 ? (int)q.y : i == 2 ? (int)q.z : (int)q.w;
-                    };
-                    l[i] = w > 0 ? P(0, -1) : (h > 0 ? P(-1, 0) : 128);
-                    t[i] = h > 0 ? P(-1, 0) : l[i];
-                    L[i] = w > 1 ? P(0, -2) : l[i];
-                    tl[i] = (h > 0 && w > 0) ? P(-1, -1) : t[i];
-                    tr[i] = (h > 0 && w < sw - 1) ? P(-1, 1) : t[i];
-                    T[i] = h > 1 ? P(-2, 0) : t[i];
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < CT; ++i) {
-                int hash = lut.a[clamp8(l[i] - tl[i]) + 128] + lut.b[clamp8(tl[i] - t[i]) + 128] +
-                           lut.c[clamp8(t[i] - tr[i]) + 128] + lut.d[clamp8(L[i] - l[i]) + 128] +
-                           lut.e[clamp8(T[i] - t[i]) + 128];                           // :424-429
-                int diff = cur[i] - median3(l[i], l[i] + t[i] - tl[i], t[i]);           // :430-431
-                if (hash < 0) { hash = -hash; diff = -diff; }                           // :433-436
-                out[i] = pack_symbol(hash, diff);
-                bins += diff ? 2u * (31 - __clz(abs(diff))) + 3u : 1u;
-            }
+        uint32_t* out = img_out + ((size_t)y0 * g.W + (size_t)x0 * sh) * CT + ((size_t)h * sw + w) * CT;
+        const int sy = ly + kHaloT, sx = lx + kHaloL;
+        const int4 pc = tile[sy][sx];
+        int4 pl, pL, ptl, pt, ptr, pT;
+        if (w >= 2 && w < sw - 1 && h >= 2) {                           // interior of the slice
+            pl = tile[sy][sx - 1]; pL = tile[sy][sx - 2];
+            ptl = tile[sy - 1][sx - 1]; pt = tile[sy - 1][sx]; ptr = tile[sy - 1][sx + 1];
+            pT = tile[sy - 2][sx];
+        } else {                                                        // llcomp.hpp:417-422, all planes at once
+            const int4 c128 = make_int4(128, 128, 128, 128);
+            pl = w > 0 ? tile[sy][sx - 1] : (h > 0 ? tile[sy - 1][sx] : c128);
+            pt = h > 0 ? tile[sy - 1][sx] : pl;
+            pL = w > 1 ? tile[sy][sx - 2] : pl;
+            ptl = (h > 0 && w > 0) ? tile[sy - 1][sx - 1] : pt;
+            ptr = (h > 0 && w < sw - 1) ? tile[sy - 1][sx + 1] : pt;
+            pT = h > 1 ? tile[sy - 2][sx] : pt;
         }
-        if (slice_bins && bins) {
+        const int cur[4] = {pc.x, pc.y, pc.z, pc.w};
+        const int l[4] = {pl.x, pl.y, pl.z, pl.w}, L[4] = {pL.x, pL.y, pL.z, pL.w};
+        const int tl[4] = {ptl.x, ptl.y, ptl.z, ptl.w}, t[4] = {pt.x, pt.y, pt.z, pt.w};
+        const int tr[4] = {ptr.x, ptr.y, ptr.z, ptr.w}, T[4] = {pT.x, pT.y, pT.z, pT.w};
+        unsigned bins = 0;
+#pragma unroll
+        for (int i = 0; i < CT; ++i) {
+            int hash = lut.a[lut_index(l[i] - tl[i])] + lut.b[lut_index(tl[i] - t[i])] +
+                       lut.c[lut_index(t[i] - tr[i])] + lut.d[lut_index(L[i] - l[i])] +
+                       lut.e[lut_index(T[i] - t[i])];                                   // :424-429
+            int diff = cur[i] - median3(l[i], l[i] + t[i] - tl[i], t[i]);               // :430-431
+            if (hash < 0) { hash = -hash; diff = -diff; }                               // :433-436
+            out[i] = pack_symbol(hash, diff);
+            if (kCount) bins += diff ? 2u * (31 - __clz(abs(diff))) + 3u : 1u;
+        }
+        if (kCount) {
             const unsigned slice = (unsigned)img * g.slices_per_image() + ty * g.tiles_x + tx;
             if (slice == primary) acc += bins;
             else atomicAdd(slice_bins + slice, (unsigned long long)bins);
         }
     }
-    if (slice_bins) {                                                   // uniform per call
+    if (kCount) {
         const unsigned sum = __reduce_add_sync(0xFFFFFFFFu, acc);
-        if ((tid & 31) == 0 && sum) atomicAdd(&cta_bins, sum);
+        if (lane == 0 && sum) atomicAdd(&cta_bins, sum);
         __syncthreads();
         if (tid == 0 && cta_bins) atomicAdd(slice_bins + primary, (unsigned long long)cta_bins);
     }
@@ -239,10 +240,12 @@ __global__ void __launch_bounds__(256) k_frontend_tiled(const uint8_t* __restric
 cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, unsigned long long* d_slice_bins,
                             cudaStream_t st) {
     if (g.H > 65535 * kTileH || g.n_images > 65535) return cudaErrorInvalidValue;
-    if ((g.C == 3 || g.C == 4) && !getenv("LLCOMP_FRONTEND_SIMPLE")) {
+    if ((g.C == 3 || g.C == 4) && g.th >= kTileH && !getenv("LLCOMP_FRONTEND_SIMPLE")) {
         dim3 grid((g.W + kTileW - 1) / kTileW, (g.H + kTileH - 1) / kTileH, g.n_images);
-        if (g.C == 3) k_frontend_tiled<3><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, d_slice_bins);
-        else k_frontend_tiled<4><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, d_slice_bins);
+        if (g.C == 3 && d_slice_bins) k_frontend_tiled<3, true><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, d_slice_bins);
+        else if (g.C == 3) k_frontend_tiled<3, false><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, nullptr);
+        else if (d_slice_bins) k_frontend_tiled<4, true><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, d_slice_bins);
+        else k_frontend_tiled<4, false><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, nullptr);
         return cudaGetLastError();
     }
     dim3 block(256);
