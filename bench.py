@@ -329,8 +329,14 @@ def main():
         kernels.append({"name": name, "ms": ms, "share_of_step": ms / step_ms, "algorithmic_bytes": alg[name],
                         "achieved_GBps": ach, "frac_of_hbm_peak": ach / peak})
     dom = max((k for k in kernels if k["name"] != "slice_decoder"), key=lambda k: k["ms"])
+    # DRAM bytes per launch from the ncu --set full capture of this exact workload (profiles/r01_v7_ncu_encode_summary.json:
+    # dram__bytes_read.sum + dram__bytes_write.sum); only quoted when the run IS that workload.
+    ncu_traffic = {"slice_coder": 13.677075e9 + 2.949559e9, "frontend": 3.221430e9 + 12.856723e9}
+    is_profiled_workload = (n_img, W, H, C, args.tile, args.noise) == (1024, 1024, 1024, 3, 0, 4)
+    for k in kernels:
+        k["ncu_dram_bytes"] = ncu_traffic.get(k["name"]) if is_profiled_workload else None
     roofline = {"kernel": dom["name"], "bound": "hbm", "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                "frac": dom["frac_of_hbm_peak"], "traffic": dom["ncu_dram_bytes"], "peak_source": peak_src,
                 "note": "slice_coder holds one serial dependency chain per slice (issue/latency-bound, not HBM-bound); "
                         "the HBM-bound kernel of the path is `frontend`, listed under kernels[]"}
 

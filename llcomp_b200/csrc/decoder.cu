@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
                                 low = (low << 8) + nextb;
                                 ++pos;
                                 nextb = ring[pos & (kRing - 1)];                             // needed at the NEXT refill
+                                asm volatile("" ::: "memory");       // keep this a branch: one decision in ten refills
                             }
                             const uint32_t ns = __byte_perm(e, 0, 0x4441 + bit);
                             half = __byte_perm(half, ns, kB == 0 ? 0x3214 : kB == 1 ? 0x3240 : kB == 2 ? 0x3410 : 0x4210);
