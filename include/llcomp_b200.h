@@ -119,8 +119,8 @@ int llcomp_b200_stage_times(llcomp_ctx *ctx, float *ms_out /* LLCOMP_B200_N_STAG
 const char *llcomp_b200_stage_name(int stage);
 /* Binary decisions coded by the last encode call on this context (bins/s reporting). */
 uint64_t llcomp_b200_last_bin_count(const llcomp_ctx *ctx);
-/* Bytes of HBM the encoder's bin queue (model pass -> range pass) may take; default 40 % of the device.
- * The slices of one call are coded in as few launch groups as fit.  Tests shrink it to force several groups. */
+/* Only for the two-kernel coder kept behind LLCOMP_CODER_SPLIT=1 (the default fused coder has no queue):
+ * bytes of HBM its bin queue may take; default 40 % of the device.  Tests shrink it to force launch groups. */
 void llcomp_b200_set_queue_budget(llcomp_ctx *ctx, uint64_t bytes);
 /* Model table entry of state s: P(bit=1)*256 | next_if_mps<<8 | next_if_lps<<16 (llcomp.hpp:252-281). */
 uint32_t llcomp_b200_debug_table(int s);
