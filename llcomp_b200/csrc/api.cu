@@ -316,7 +316,7 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
             StageScope sc(ctx, st, kStFrontend);
             CK(launch_frontend(d_pixels, g, ctx->sym.p, nullptr, st));
         }
-        const uint64_t gsb = model_global_state_bytes(ns);
+        const uint64_t gsb = fused_global_state_bytes(ns);
         if (gsb) CK(ctx->gstate.reserve(gsb));
         {
             StageScope sc(ctx, st, kStRange);

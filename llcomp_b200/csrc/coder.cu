@@ -8,13 +8,15 @@
 // The reference interleaves two recurrences per binary decision; they are independent of each other:
 //   (a) the probability state of context (hash, ctx) depends only on the earlier bits of THAT context;
 //   (b) low/range of the coder depend on the (bit, probability) sequence, not on the states.
-// K2a  k_model_pass   one warp per slice, the slice's 63,408 state bytes in shared memory.  32 samples per
-//                     step, one per lane; lanes whose samples share a context are chained in sample order
-//                     (match.any groups, the group leader walks its members with the 8 sub-states in
-//                     registers).  Emits one 16-bit entry per decision into the bin queue in HBM.
-// K2b  k_range_pass   the irreducible serial chain: x = range*M + A, renormalise, carry/byte emission.
-//                     No shared-memory state, so every slice of the batch is resident at once; S slices
-//                     share a warp (32/S lanes each) when there are more slices than schedulers.
+// and (b) itself splits into the range recurrence (serial, 4 instructions per decision) and the low/carry/byte
+// side, which is a sum of per-decision increments between renormalisations and runs lane-parallel.
+//
+//   k_slice_coder_fused   default.  One CTA per slice, three warps: model (a), range chain, bytes; the warps hand
+//                         256..512-decision blocks to each other through shared memory.
+//   k_model_pass + k_range_pass_ws   the same work as two kernels with a 2-byte-per-decision queue in HBM
+//                         between them (LLCOMP_CODER_SPLIT=1; kept as a cross-check of the fused kernel).
+// The slice's 63,408 bytes of state rows live in shared memory while every slice of the launch finds a slot,
+// else in global memory behind L1.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -30,23 +32,14 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 //   bit 1: M = P,       A = 0     range' = (range*M + A) >> 8 = range*P >> 8                (llcomp.hpp:62,69)
 //   bit 0: M = 256 - P, A = 255   range' = range - (range*P >> 8) = ceil(range*(256-P)/256)   (llcomp.hpp:66)
 // and low += range - range' exactly when the decision is a 1 (llcomp.hpp:68).  P is in [7,247], so M fits a byte.
-// The front end counts the decisions of every slice exactly, so the host lays the queue out without slack
-// beyond kQueuePad entries per slice (16-byte alignment, whole-vector reads of the last partial vector).
+// In the split form the front end counts the decisions of every slice exactly, so the host lays the queue out
+// without slack beyond kQueuePad entries per slice (16-byte alignment, reads of the last partial vector).
 
 // ---------------------------------------------------------------------------------------------------
-// K2a
+// Model pass
 // ---------------------------------------------------------------------------------------------------
-// The contexts of a slice are split into K classes by hash % K; each class is evolved by its own CTA (one warp)
-// with only its share of the state in shared memory (63,408 / K bytes).  Classes never interact -- a context's
-// state depends on that context's decisions only -- so the K warps of a slice need no synchronisation; each
-// scans all records of the slice (the decision offsets are a prefix sum over all of them) and processes its own.
-// More, smaller CTAs per SM is what hides the shared-memory latency chains of this pass.
-template <int K>
-struct ModelShape {
-    static constexpr int kRows = (kContexts + K - 1) / K;
-    static constexpr int kRowBytes = (kRows * 8 + 15) & ~15;
-    static constexpr int kSmem = kRowBytes + 256 * 4;
-};
+constexpr int kRowBytesSmem = kStateBytes;                   // 7926 rows x 8 sub-states, a multiple of 16
+constexpr int kModelSmem = kRowBytesSmem + 256 * 4;          // + tab2
 
 // Where the model pass puts its 16-bit entries: the bin queue in HBM (split kernels) or a shared-memory FIFO
 // (fused kernel).  `pos` counts from the first decision of the current 32-sample step.
@@ -54,7 +47,7 @@ struct QueueSink {
     uint16_t* q;
     __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { q[pos] = (uint16_t)w; }
 };
-constexpr int kFifo = 2048;                                  // entries; a multiple of the 256-decision block
+constexpr int kFifo = 4096;                                  // entries; a multiple of the decision block
 struct FifoSink {
     uint16_t* fifo;
     uint32_t base;
@@ -63,8 +56,8 @@ struct FifoSink {
 
 // One step of the model pass: 32 consecutive samples, one per lane (rec = packed record of this lane's sample).
 // Returns the number of decisions the step produced.  llcomp.hpp:166-206 (binarisation), :440-443 (state).
-template <int K, class Sink>
-__device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint32_t cls, uint2* state,
+template <class Sink>
+__device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint2* state,
                                                 const uint32_t* tab2, int lane, Sink sink) {
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t hash = rec >> 11;
@@ -82,14 +75,14 @@ __device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint32
         total += __popc(m) << b;
     }
 
-    // lanes of this class with the same context form a chain; its first lane carries the row through the members
-    const bool mine = valid && (hash % K) == cls;
+    // lanes with the same context form a chain; its first lane carries the row through the members
+    const bool mine = valid;
     const uint32_t key = mine ? hash : (0x10000u | lane);
     uint32_t members = __match_any_sync(kFull, key);
     const int head = __ffs(members) - 1;
     const bool leader = mine && head == lane;
     uint2 row = make_uint2(0, 0);
-    if (leader) row = state[hash / K];
+    if (leader) row = state[hash];
     // Smooth content: every member of the chain has a zero residual (one decision, "is zero" = 1, sub-state 0) and
     // that sub-state sits in the saturated state 127 (MPS 1, next-if-MPS 127, llcomp.hpp:258).  Then every member
     // gets the same entry and the row does not change: no need to walk the chain member by member.
@@ -143,7 +136,7 @@ __device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint32
         }
     }
     if (leader)
-        state[hash / K] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
+        state[hash] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
                                      s4b | (s5b << 8) | (s6b << 16) | (s7b << 24));
     __syncwarp();
     return total;
@@ -159,23 +152,22 @@ __device__ __forceinline__ void fill_tab2(uint32_t* tab2, int lane) {
     }
 }
 
-// kGlobalState (K == 1): the rows live in global memory, pre-zeroed by the host, and are reached through L1
+// kGlobalState: the rows live in global memory, pre-zeroed by the host, and are reached through L1
 // (116 vs 97 cycles per dependent read-modify-write, profiles/microbench/l1_rmw.cu); without 63 KB of shared
 // memory per slice every slice of a 1024-image batch is resident at once.
-template <int K, bool kGlobalState = false>
+template <bool kGlobalState>
 __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ sym, Geom g, uint64_t s0,
                                                    uint16_t* __restrict__ queue,
                                                    const uint64_t* __restrict__ q_off,
                                                    uint2* __restrict__ gstate) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kRowBytes = kGlobalState ? 0 : ModelShape<K>::kRowBytes;
+    constexpr int kRowBytes = kGlobalState ? 0 : kRowBytesSmem;
     uint2* state = kGlobalState ? gstate + (size_t)blockIdx.x * kContexts
-                                : reinterpret_cast<uint2*>(smem);         // one 8-byte row per context of the class
+                                : reinterpret_cast<uint2*>(smem);         // one 8-byte row per context
     uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kRowBytes);       // [state*2 + bit] = entry | next << 16
 
     const int lane = threadIdx.x;
-    const uint32_t cls = blockIdx.x % K;
-    const uint64_t s = s0 + blockIdx.x / K;
+    const uint64_t s = s0 + blockIdx.x;
     const Slice sl = slice_of(g, s);
     const uint32_t* in = sym + sl.sym_off;
     const uint64_t n = sl.n;
@@ -193,7 +185,7 @@ __global__ void __launch_bounds__(32) k_model_pass(const uint32_t* __restrict__ 
             const uint64_t k = base + 32 + lane;
             rec_next = k < n ? in[k] : 0u;                                // next step's record flies under this step
         }
-        q += model_chunk<K>(rec, valid, cls, state, tab2, lane, QueueSink{q});
+        q += model_chunk(rec, valid, state, tab2, lane, QueueSink{q});
     }
 }
 
@@ -249,156 +241,8 @@ __device__ __forceinline__ void shift_low(ByteTail& t) {
     t.low = (t.low & 0xFFu) << 8;
 }
 
-// One decision the plain way (llcomp.hpp:60-73 in the (M, A) form above); used outside the pipelined loop.
-__device__ __forceinline__ void put_simple(ByteTail& t, uint32_t& range, uint32_t m, uint32_t a, bool is_one) {
-    const uint32_t x = range * m + a;
-    const uint32_t r = x >> 8;
-    if (is_one) t.low += range - r;
-    range = r;
-    if (x < 0x10000u) {                                      // range' < 0x100 (and >= 1): one step renormalises
-        shift_low(t);
-        range = r << 8;
-    }
-}
-
-// m, a as above; one = 1 when the decision is a 1 (A is 0x00 then, 0xFF otherwise).
-struct Entry { uint32_t m, a, one; };
-__device__ __forceinline__ Entry entry_lo(uint32_t w) {
-    const uint32_t a = prmt(w, 0x4449);
-    return {w & 0xFFu, a, ~a & 1u};
-}
-__device__ __forceinline__ Entry entry_hi(uint32_t w) {
-    const uint32_t a = prmt(w, 0x444B);
-    return {prmt(w, 0x4442), a, ~a & 1u};
-}
-
-constexpr int kRangeWarps = 4;      // warps per CTA of the range pass: one per scheduler of the SM
-
-template <int S, int ACT = 32>
-__global__ void __launch_bounds__(32 * kRangeWarps) k_range_pass(const uint16_t* __restrict__ queue,
-                                                   const uint64_t* __restrict__ q_off,
-                                                   const unsigned long long* __restrict__ n_bins, Geom g, uint64_t s0,
-                                                   uint32_t n_launch, uint8_t* __restrict__ scratch,
-                                                   uint32_t* __restrict__ slice_bytes, int* __restrict__ status) {
-    constexpr int L = 32 / S;                                // lanes per slice
-    __shared__ uint4 stage_all[kRangeWarps][2][32];
-    __shared__ __align__(16) uint32_t psum_all[kRangeWarps][S][8];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / L, sub = lane % L;
-    if (lane >= ACT) return;                                 // experiment: the surplus lanes are redundant for S == 1
-    constexpr unsigned kAct = ACT == 32 ? 0xFFFFFFFFu : ((1u << ACT) - 1u);
-    uint4 (*stage)[32] = stage_all[warp];
-    // slice of this lane group; surplus groups of the last warps shadow the last slice (same bytes, same place)
-    const uint32_t k = min((blockIdx.x * kRangeWarps + warp) * S + grp, n_launch - 1);
-    const uint64_t s = s0 + k;
-    const Slice sl = slice_of(g, s);
-    const uint4* src = reinterpret_cast<const uint4*>(queue + q_off[s]);
-    const uint64_t nb = n_bins[s];
-    const uint32_t n_vec = (uint32_t)(nb / 8);               // whole 8-entry vectors of this slice
-    // the pipelined loop runs while every slice of the warp has vectors left; the rest goes one entry at a time
-    const uint32_t n_common = __reduce_min_sync(kAct, n_vec);
-
-    uint8_t* const out0 = scratch + scratch_off(sl, s);
-    uint8_t* const out_end = out0 + scratch_cap(sl);
-    ByteTail t;
-    t.low = 0; t.hp = kHpEmpty; t.outp = out0;               // llcomp.hpp:35
-    uint32_t range = 0xFF00u;
-    bool overflow = false;
-    // A slice that outgrows its scratch stops storing: it rewinds to the start of its scratch (the bytes are
-    // void anyway) and raises the overflow status at the end.
-    auto guard = [&](uint32_t upcoming) {
-        if (t.outp + (t.hp >> 9) + upcoming + 16 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
-    };
-
-    // Per 8-entry vector, two stages.  Stage A is the range recurrence alone, straight-line and branch-free
-    // (x = range*M + A; range' = x < 0x10000 ? x & ~0xFF : x >> 8), with the running sum of the low increments
-    // and a bit mask of the decisions that renormalised computed in its shadow.  Stage B replays the byte/carry
-    // side at those decisions only; its loop runs on a warp-uniform mask (REDUX), so its branches are uniform.
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    constexpr int PER = 32 / ACT;                            // vectors each active lane stages per refill
-    uint4 r0[PER], r1[PER];
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const uint32_t v0 = sub + q * ACT;
-        r0[q] = v0 < n_common && v0 < (uint32_t)L ? src[v0] : zero4;
-        r1[q] = L + v0 < n_common && v0 < (uint32_t)L ? src[L + v0] : zero4;
-    }
-    const uint32_t n_blocks = (n_common + L - 1) / L;
-    uint32_t* const my_psum = &psum_all[warp][grp][0];
-    for (uint32_t b = 0; b < n_blocks; ++b) {
-#pragma unroll
-        for (int q = 0; q < PER; ++q) stage[b & 1][lane + q * ACT] = r0[q];
-        __syncwarp(kAct);
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            r0[q] = r1[q];
-            const uint64_t v = (uint64_t)(b + 2) * L + sub + q * ACT;   // two refills ahead of the chain
-            r1[q] = v < n_common && sub + q * ACT < L ? src[v] : zero4;
-        }
-        guard(L * 8);         // a block emits at most one byte per decision plus the bytes deferred so far
-        const int jn = min((uint32_t)L, n_common - b * L);
-#pragma unroll 1
-        for (int j = 0; j < jn; ++j) {
-            const uint4 w = stage[b & 1][grp * L + j];
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-            uint32_t psum[8];
-            uint32_t acc = 0, mask = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {                                 // stage A
-                const Entry e = (i & 1) ? entry_hi(ww[i >> 1]) : entry_lo(ww[i >> 1]);
-                const uint32_t x = range * e.m + e.a;
-                const uint32_t r = x >> 8;
-                acc += (range - r) * e.one;
-                psum[i] = acc;
-                const bool renorm = x < 0x10000u;
-                mask |= renorm ? (1u << i) : 0u;
-                range = renorm ? (x & 0xFFFFFF00u) : r;
-            }
-            uint32_t todo = __reduce_or_sync(kAct, mask);                // uniform: union over the warp's slices
-            if (todo) {                                                   // stage B
-                *reinterpret_cast<uint4*>(my_psum) = make_uint4(psum[0], psum[1], psum[2], psum[3]);
-                *reinterpret_cast<uint4*>(my_psum + 4) = make_uint4(psum[4], psum[5], psum[6], psum[7]);
-                __syncwarp(kAct);
-                uint32_t rebase = t.low;                                  // low == rebase + psum[.] between renorms
-                do {
-                    const int i = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    if (S == 1 || ((mask >> i) & 1u)) {
-                        const uint32_t p = my_psum[i];
-                        t.low = rebase + p;
-                        shift_low(t);
-                        rebase = t.low - p;
-                    }
-                } while (todo);
-                t.low = rebase;
-                __syncwarp(kAct);
-            }
-            t.low += acc;
-        }
-    }
-
-    // the entries beyond the common part (other slices of the warp were shorter, and the nb % 8 tail)
-    {
-        const uint16_t* tq = reinterpret_cast<const uint16_t*>(src) + (uint64_t)n_common * 8;
-        const uint64_t left = nb - (uint64_t)n_common * 8;
-        for (uint64_t i = 0; i < left; ++i) {
-            if ((i & 63) == 0) guard(64);
-            const uint32_t e = tq[i];
-            put_simple(t, range, e & 0xFFu, (e & 0x8000u) ? 255u : 0u, !(e & 0x8000u));
-        }
-    }
-    guard(0);
-    // finish(), llcomp.hpp:75-81: range = 0xFF both times, so each renorm_encoder call shifts exactly once
-    t.low += 0xFFu;
-    shift_low(t);
-    shift_low(t);
-    if (sub == 0) {                                                       // shadows write the same value
-        slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(t.outp - out0);
-        if (overflow) atomicCAS(status, kDevOk, kDevOverflow);
-    }
-}
-
-constexpr int kBlk = 256;                                    // decisions per block of the warp-specialised passes
+constexpr int kBlk = 256;                                    // decisions per block of the split range pass
+constexpr int kBlkF = 512;                                   // decisions per block of the fused coder
 
 // Byte side of one block of `cnt` decisions (helper warp, lane-parallel over 32 decisions at a time): x values
 // from the chain, A operands (0 <=> the decision is a 1) from the operand ring.  Exact re-statement of the
@@ -491,7 +335,7 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
                                                       const uint64_t* __restrict__ q_off,
                                                       const unsigned long long* __restrict__ n_bins, Geom g, uint64_t s0,
                                                       uint8_t* __restrict__ scratch, uint32_t* __restrict__ slice_bytes,
-                                                      int* __restrict__ status, int debug_skip) {
+                                                      int* __restrict__ status) {
     __shared__ __align__(16) uint2 in_ring[2][kBlk + 4];     // (M, A) per decision (+ slack for the look-ahead load)
     __shared__ __align__(16) uint32_t x_ring[2][kBlk];       // x per decision
 
@@ -542,7 +386,7 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
 
     for (uint32_t b = 0; b <= n_blk; ++b) {                  // iteration b: chain on block b, helper on block b-1
         if (is_chain) {
-            if (b < n_blk && debug_skip != 1) {
+            if (b < n_blk) {
                 const uint32_t cnt = (uint32_t)min((uint64_t)kBlk, nb - (uint64_t)b * kBlk);
                 const uint4* in = reinterpret_cast<const uint4*>(in_ring[b & 1]);
                 uint4* xo = reinterpret_cast<uint4*>(x_ring[b & 1]);
@@ -563,7 +407,7 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
                 }
             }
         } else {
-            if (b > 0 && debug_skip != 2) {                  // byte side of block b-1
+            if (b > 0) {                                     // byte side of block b-1
                 const uint32_t pb = b - 1;
                 const uint32_t cnt = (uint32_t)min((uint64_t)kBlk, nb - (uint64_t)pb * kBlk);
                 byte_side_block(t, overflow, x_carry, x_ring[pb & 1], in_ring[pb & 1], cnt, lane, out0, out_end);
@@ -608,14 +452,14 @@ __global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __res
                                                           uint32_t* __restrict__ slice_bytes, int* __restrict__ status,
                                                           uint2* __restrict__ gstate) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kRowBytes = kGlobalState ? 0 : ModelShape<1>::kRowBytes;
+    constexpr int kRowBytes = kGlobalState ? 0 : kRowBytesSmem;
     uint2* state = kGlobalState ? gstate + (size_t)blockIdx.x * kContexts : reinterpret_cast<uint2*>(smem);
     uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kRowBytes);
     uint16_t* fifo = reinterpret_cast<uint16_t*>(smem + kRowBytes + 1024);
-    uint2 (*in_ring)[kBlk + 4] = reinterpret_cast<uint2 (*)[kBlk + 4]>(smem + kRowBytes + 1024 + kFifo * 2);
-    uint32_t (*x_ring)[kBlk] = reinterpret_cast<uint32_t (*)[kBlk]>(smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlk + 4) * 8);
+    uint2 (*in_ring)[kBlkF + 4] = reinterpret_cast<uint2 (*)[kBlkF + 4]>(smem + kRowBytes + 1024 + kFifo * 2);
+    uint32_t (*x_ring)[kBlkF] = reinterpret_cast<uint32_t (*)[kBlkF]>(smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlkF + 4) * 8);
     volatile unsigned long long* ctl = reinterpret_cast<volatile unsigned long long*>(
-        smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlk + 4) * 8 + 2 * kBlk * 4);
+        smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4);
     // Control words, double buffered by iteration parity p: ctl[2p] = decisions produced so far,
     // ctl[2p+1] = 1 once the model warp has seen every sample.  Written by the model warp before the barrier
     // that opens iteration p, read by everybody right after it.
@@ -650,7 +494,7 @@ __global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __res
             const bool valid = base + lane < n;
             const uint64_t k = base + 32 + lane;
             rec_next = k < n ? in[k] : 0u;
-            produced += model_chunk<1>(rec, valid, 0u, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
+            produced += model_chunk(rec, valid, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
             base += 32;
         }
         if (lane == 0) { ctl[2 * (for_iter & 1)] = produced; ctl[2 * (for_iter & 1) + 1] = base >= n ? 1ull : 0ull; }
@@ -667,16 +511,20 @@ __global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __res
     uint32_t range = 0xFF00u;
 
     auto expand = [&](uint32_t blk) {                        // helper: FIFO entries of block blk -> (M, A) operands
-        const uint4 e = *reinterpret_cast<const uint4*>(fifo + ((blk * kBlk) & (kFifo - 1)) + lane * 8);
-        const uint32_t w[4] = {e.x, e.y, e.z, e.w};
-        uint4* dst = reinterpret_cast<uint4*>(&in_ring[blk & 1][lane * 8]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            dst[k] = make_uint4(w[k] & 0xFFu, prmt(w[k], 0x4449), prmt(w[k], 0x4442), prmt(w[k], 0x444B));
+        for (int h = 0; h < kBlkF / 256; ++h) {              // 8 entries per lane and pass
+            const int at = h * 256 + lane * 8;
+            const uint4 e = *reinterpret_cast<const uint4*>(fifo + ((blk * kBlkF) & (kFifo - 1)) + at);
+            const uint32_t w[4] = {e.x, e.y, e.z, e.w};
+            uint4* dst = reinterpret_cast<uint4*>(&in_ring[blk & 1][at]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                dst[k] = make_uint4(w[k] & 0xFFu, prmt(w[k], 0x4449), prmt(w[k], 0x4442), prmt(w[k], 0x444B));
+        }
     };
 
     // prime: three blocks of decisions, block 0 expanded
-    if (role == 1) produce_until(3 * kBlk, 0);
+    if (role == 1) produce_until(3 * kBlkF, 0);
     trio_sync();
     if (role == 2) expand(0);
     trio_sync();
@@ -687,9 +535,9 @@ __global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __res
         const bool fin = ctl[2 * (b & 1) + 1] != 0;
         // number of decisions of block k known to exist: 256 unless finished and it is the last, partial one
         auto block_count = [&](uint32_t k) -> int {          // <= 0: the block does not exist
-            if (!fin) return kBlk;
-            const long long left = (long long)prod - (long long)k * kBlk;
-            return left > kBlk ? kBlk : (int)left;
+            if (!fin) return kBlkF;
+            const long long left = (long long)prod - (long long)k * kBlkF;
+            return left > kBlkF ? kBlkF : (int)left;
         };
         const int cnt_prev = b > 0 ? block_count(b - 1) : 0;
         const int cnt_cur = block_count(b);
@@ -716,7 +564,7 @@ __global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __res
                 }
             }
         } else if (role == 1) {
-            produce_until((uint64_t)(b + 4) * kBlk, b + 1);
+            produce_until((uint64_t)(b + 4) * kBlkF, b + 1);
         } else {
             if (cnt_prev > 0) byte_side_block(t, overflow, x_carry, x_ring[(b - 1) & 1], in_ring[(b - 1) & 1],
                                               (uint32_t)cnt_prev, lane, out0, out_end);
@@ -738,19 +586,25 @@ __global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __res
     }
 }
 
-constexpr int kFusedSmemNoState = 1024 + kFifo * 2 + 2 * (kBlk + 4) * 8 + 2 * kBlk * 4 + 32;
+constexpr int kFusedSmemNoState = 1024 + kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4 + 32;
+
+// The fused CTA with the state rows in shared memory takes 85 KB: 2 per SM.  Beyond 2 x 148 slices the rows go
+// behind L1 so that the whole launch is resident at once.
+uint64_t fused_global_state_bytes(uint64_t n_slices) {
+    return (n_slices > 2 * 148 && !getenv("LLCOMP_MODEL_SMEM_STATE")) ? n_slices * (uint64_t)kStateBytes : 0;
+}
 
 cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                                      int* d_status, uint8_t* d_gstate, cudaStream_t st) {
     const uint64_t ns = g.n_slices();
     if (ns == 0 || ns > 0x0FFFFFFFull) return cudaErrorInvalidValue;
-    if (model_global_state_bytes(ns)) {
+    if (fused_global_state_bytes(ns)) {
         cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);      // all states start at 0
         if (e != cudaSuccess) return e;
         k_slice_coder_fused<true><<<(unsigned)ns, 128, kFusedSmemNoState, st>>>(d_sym, g, d_scratch, d_slice_bytes,
                                                                                  d_status, reinterpret_cast<uint2*>(d_gstate));
     } else {
-        k_slice_coder_fused<false><<<(unsigned)ns, 128, kFusedSmemNoState + ModelShape<1>::kRowBytes, st>>>(
+        k_slice_coder_fused<false><<<(unsigned)ns, 128, kFusedSmemNoState + kRowBytesSmem, st>>>(
             d_sym, g, d_scratch, d_slice_bytes, d_status, nullptr);
     }
     return cudaGetLastError();
@@ -758,10 +612,9 @@ cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8
 
 // ---------------------------------------------------------------------------------------------------
 cudaError_t configure_slice_coder() {
-    cudaError_t e = cudaFuncSetAttribute(k_model_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<1>::kSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_model_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModelShape<2>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_model_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModelSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   kFusedSmemNoState + ModelShape<1>::kRowBytes);
+                                                   kFusedSmemNoState + kRowBytesSmem);
     return e;
 }
 
@@ -777,18 +630,10 @@ cudaError_t launch_model_pass(const uint32_t* d_sym, const Geom& g, uint64_t s0,
     if (model_global_state_bytes(count)) {
         cudaError_t e = cudaMemsetAsync(d_gstate, 0, count * (uint64_t)kStateBytes, st);   // all states start at 0
         if (e != cudaSuccess) return e;
-        k_model_pass<1, true><<<n, 32, 256 * 4, st>>>(d_sym, g, s0, d_queue, d_qoff, reinterpret_cast<uint2*>(d_gstate));
+        k_model_pass<true><<<n, 32, 256 * 4, st>>>(d_sym, g, s0, d_queue, d_qoff, reinterpret_cast<uint2*>(d_gstate));
         return cudaGetLastError();
     }
-    int K = 1;
-    if (const char* e = getenv("LLCOMP_MODEL_K")) K = atoi(e);            // tuning knob (hash-class partition)
-    switch (K) {
-        case 1: k_model_pass<1><<<n, 32, ModelShape<1>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
-        case 2: k_model_pass<2><<<n * 2, 32, ModelShape<2>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
-        case 4: k_model_pass<4><<<n * 4, 32, ModelShape<4>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
-        case 8: k_model_pass<8><<<n * 8, 32, ModelShape<8>::kSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr); break;
-        default: return cudaErrorInvalidValue;
-    }
+    k_model_pass<false><<<n, 32, kModelSmem, st>>>(d_sym, g, s0, d_queue, d_qoff, nullptr);
     return cudaGetLastError();
 }
 
@@ -799,28 +644,7 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
     // One slice per warp while every warp can have a scheduler of its own (4 x 148 of them); beyond that slices
     // share warps: the chain is latency-bound, so a second slice in the same warp is nearly free.
     const unsigned n = (unsigned)count;
-    if (!getenv("LLCOMP_RANGE_LOCKSTEP")) {                               // default: warp-specialised form
-        int skip = 0;                                                      // timing experiments only (1: no chain, 2: no byte side)
-        if (const char* e = getenv("LLCOMP_WS_SKIP")) skip = atoi(e);
-        k_range_pass_ws<<<n, 128, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, d_scratch, d_slice_bytes, d_status, skip);
-        return cudaGetLastError();
-    }
-    int S = n <= 1536 ? 1 : n <= 3072 ? 2 : 4;            // measured on B200: ~2 warps per scheduler is the knee
-    if (const char* e = getenv("LLCOMP_RANGE_S")) S = atoi(e);            // tuning knob
-    const unsigned per_cta = kRangeWarps * S, ctas = (n + per_cta - 1) / per_cta;
-    const dim3 blk(32 * kRangeWarps);
-    int act = 32;
-    if (const char* e = getenv("LLCOMP_RANGE_ACT")) act = atoi(e);        // experiment
-    if (S == 1 && act == 16) { k_range_pass<1, 16><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); return cudaGetLastError(); }
-    if (S == 1 && act == 8) { k_range_pass<1, 8><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); return cudaGetLastError(); }
-    if (S == 1 && act == 1) { k_range_pass<1, 1><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); return cudaGetLastError(); }
-    switch (S) {
-        case 1: k_range_pass<1><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
-        case 2: k_range_pass<2><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
-        case 4: k_range_pass<4><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
-        case 8: k_range_pass<8><<<ctas, blk, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, n, d_scratch, d_slice_bytes, d_status); break;
-        default: return cudaErrorInvalidValue;
-    }
+    k_range_pass_ws<<<n, 128, 0, st>>>(d_queue, d_qoff, d_nbins, g, s0, d_scratch, d_slice_bytes, d_status);
     return cudaGetLastError();
 }
 

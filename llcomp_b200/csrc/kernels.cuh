@@ -22,6 +22,7 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
 //     queue in HBM.  d_gstate holds the state rows when the launch has more slices than shared-memory slots.
 cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                                      int* d_status, uint8_t* d_gstate, cudaStream_t st);
+uint64_t fused_global_state_bytes(uint64_t n_slices);
 cudaError_t configure_slice_coder();
 
 // K3  exclusive scan of slice byte counts; K4 compaction into one contiguous payload (pack.cu)
