@@ -158,15 +158,37 @@ __global__ void __launch_bounds__(256, 6) k_frontend_tiled(const uint8_t* __rest
         reinterpret_cast<uint4*>(&lut)[tid] = reinterpret_cast<const uint4*>(&c_quant_luts)[tid];
     // stage the planes (llcomp.hpp:396-409): warp w takes rows w, w+8, w+16; coordinates clamped to the image
     // (clamped copies are never used as neighbours of a valid in-slice pixel)
-    for (int sy = warp; sy < kSmemH; sy += 8) {
-        const int y = min(max(ry0 + sy - kHaloT, 0), g.H - 1);
-        const uint8_t* rowp = base + (size_t)y * pitch;
-        for (int sx = lane; sx < kSmemW; sx += 32) {
-            const int x = min(max(rx0 + sx - kHaloL, 0), g.W - 1);
-            const uint8_t* p = rowp + x * CT;
-            const int gg = p[1];
-            const int r = (int)p[0] - gg, b = (int)p[2] - gg;
-            tile[sy][sx] = make_int4(r, gg + (b + r) / 4, b, CT == 4 ? (int)p[3] : 0);
+    // (all loads of a thread are issued before the first use: 3 rows x 3 columns, fully unrolled)
+    {
+        uint8_t raw[3][3][4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int sy = warp + 8 * a;
+            const int y = min(max(ry0 + sy - kHaloT, 0), g.H - 1);
+            const uint8_t* rowp = base + (size_t)y * pitch;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const int sx = lane + 32 * b;
+                const int x = min(max(rx0 + sx - kHaloL, 0), g.W - 1);
+                const uint8_t* p = rowp + x * CT;
+                if (sy < kSmemH && sx < kSmemW) {
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) raw[a][b][c] = p[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int sy = warp + 8 * a;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const int sx = lane + 32 * b;
+                if (sy < kSmemH && sx < kSmemW) {
+                    const int gg = raw[a][b][1];
+                    const int r = (int)raw[a][b][0] - gg, bb = (int)raw[a][b][2] - gg;
+                    tile[sy][sx] = make_int4(r, gg + (bb + r) / 4, bb, CT == 4 ? (int)raw[a][b][3] : 0);
+                }
+            }
         }
     }
     __syncthreads();
