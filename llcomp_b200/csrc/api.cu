@@ -57,6 +57,8 @@ struct DevBuf {
 struct llcomp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;          // used by the host-buffer entry points
+    static constexpr int kGroups = 4;       // host-buffer encode: image groups pipelined over this many streams
+    cudaStream_t group_stream[kGroups] = {};
     DevBuf<uint32_t> sym;                   // K1 -> K2a records
     DevBuf<unsigned long long> slice_bins;  // K1: exact number of binary decisions per slice
     DevBuf<uint64_t> qoff;                  // first bin-queue entry of every slice (within its launch group)
@@ -186,6 +188,35 @@ struct StageScope {
     ~StageScope() { if (b) cudaEventRecord(b, st); }
 };
 
+// Front end + fused coder + scan + compaction of the images [first_image, first_image + g.n_images) of a batch
+// whose workspace (records, scratch, byte counts, state rows) was reserved for the whole batch: every buffer is
+// linear in the image index, so a group of images simply works on its own stretch of each.
+int encode_fused_on(llcomp_ctx* ctx, const uint8_t* d_pixels, const Geom& g, uint64_t first_image, bool global_state,
+                    uint8_t* d_payload, uint64_t capacity, uint64_t* d_offsets, cudaStream_t st) {
+    const uint64_t spi = g.slices_per_image(), first_slice = first_image * spi;
+    uint32_t* sym = ctx->sym.p + first_image * g.image_samples();
+    uint8_t* scratch = ctx->scratch.p + first_image * (2 * g.image_samples() + kScratchSlack * spi);
+    uint32_t* slice_bytes = ctx->slice_bytes.p + first_slice;
+    uint8_t* gstate = global_state ? ctx->gstate.p + first_slice * (uint64_t)kStateBytes : nullptr;
+    {
+        StageScope sc(ctx, st, kStFrontend);
+        CK(launch_frontend(d_pixels, g, sym, nullptr, st));
+    }
+    {
+        StageScope sc(ctx, st, kStRange);
+        CK(launch_slice_coder_fused(sym, g, scratch, slice_bytes, ctx->d_status, gstate, st));
+    }
+    {
+        StageScope sc(ctx, st, kStScan);
+        CK(launch_scan(slice_bytes, g.n_slices(), d_offsets, capacity, ctx->d_status, st));
+    }
+    {
+        StageScope sc(ctx, st, kStCompact);
+        CK(launch_compact(scratch, g, d_offsets, d_payload, capacity, st));
+    }
+    return LLCOMP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -222,6 +253,8 @@ int llcomp_b200_ctx_create(int device, llcomp_ctx** out) {
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int k = 0; k < llcomp_ctx::kGroups && e == cudaSuccess; ++k)
+        e = cudaStreamCreateWithFlags(&ctx->group_stream[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int));
     if (e == cudaSuccess) {
@@ -250,6 +283,7 @@ void llcomp_b200_ctx_destroy(llcomp_ctx* ctx) {
     if (ctx->d_status) cudaFree(ctx->d_status);
     for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto& gs : ctx->group_stream) if (gs) cudaStreamDestroy(gs);
     delete ctx;
 }
 
@@ -312,17 +346,11 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
 
     if (!getenv("LLCOMP_CODER_SPLIT")) {
         // Default: front end, then ONE fused coder kernel (model + range chain + bytes per slice); fully asynchronous.
-        {
-            StageScope sc(ctx, st, kStFrontend);
-            CK(launch_frontend(d_pixels, g, ctx->sym.p, nullptr, st));
-        }
         const uint64_t gsb = fused_global_state_bytes(ns);
         if (gsb) CK(ctx->gstate.reserve(gsb));
-        {
-            StageScope sc(ctx, st, kStRange);
-            CK(launch_slice_coder_fused(ctx->sym.p, g, ctx->scratch.p, ctx->slice_bytes.p, ctx->d_status, ctx->gstate.p, st));
-        }
+        const int rc = encode_fused_on(ctx, d_pixels, g, 0, gsb != 0, d_payload, capacity, d_offsets, st);
         ctx->last_bins = 0;
+        return rc;
     } else {
     // K1: records + exact decision count of every slice
         CK(cudaMemsetAsync(ctx->slice_bins.p, 0, ns * sizeof(unsigned long long), st));
@@ -415,31 +443,94 @@ int llcomp_b200_encode_batch(llcomp_ctx* ctx, const uint8_t* pixels, const llcom
     CK(cudaSetDevice(ctx->device));
     const uint64_t ns = g.n_slices(), cap = payload_capacity(g);
     const uint32_t spi = g.slices_per_image();
+    const size_t hb = header_bytes(g);
     CK(ctx->pixels.reserve(g.n_samples()));
     CK(ctx->payload.reserve(cap));
-    CK(ctx->offsets.reserve(ns + 1));
-    cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->pixels.p, pixels, g.n_samples(), cudaMemcpyHostToDevice, st));
-    int rc = llcomp_b200_encode_device(ctx, ctx->pixels.p, gi, ctx->payload.p, cap, ctx->offsets.p, st);
-    if (rc) return rc;
-    std::vector<uint64_t> off(ns + 1);
-    CK(cudaMemcpyAsync(off.data(), ctx->offsets.p, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    rc = llcomp_b200_finish(ctx, st);
-    if (rc) return rc;
 
-    const size_t hb = header_bytes(g);
+    // Image groups pipelined over a few streams: the upload of group k+1 and the download of group k-1 run under
+    // the coding of group k, and -- the coder being latency-bound per slice -- the groups' kernels overlap each
+    // other on the GPU.  The state rows then have to live behind L1 (a shared-memory slot per slice would
+    // serialise the groups).  The split coder (LLCOMP_CODER_SPLIT) and small batches take the single-call path.
+    const int n_groups = (getenv("LLCOMP_CODER_SPLIT") || g.n_images < 2 * llcomp_ctx::kGroups) ? 1 : llcomp_ctx::kGroups;
+    if (n_groups == 1) {
+        CK(ctx->offsets.reserve(ns + 1));
+        cudaStream_t st = ctx->stream;
+        CK(cudaMemcpyAsync(ctx->pixels.p, pixels, g.n_samples(), cudaMemcpyHostToDevice, st));
+        int rc = llcomp_b200_encode_device(ctx, ctx->pixels.p, gi, ctx->payload.p, cap, ctx->offsets.p, st);
+        if (rc) return rc;
+        std::vector<uint64_t> off(ns + 1);
+        CK(cudaMemcpyAsync(off.data(), ctx->offsets.p, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        rc = llcomp_b200_finish(ctx, st);
+        if (rc) return rc;
+        uint64_t pos = 0;
+        for (int k = 0; k < g.n_images; ++k) {
+            const uint64_t p0 = off[(uint64_t)k * spi], p1 = off[(uint64_t)(k + 1) * spi];
+            offsets[k] = pos;
+            if (pos + hb + (p1 - p0) > out_cap) return LLCOMP_ERR_OVERFLOW;
+            write_header(g, &off[(uint64_t)k * spi], out + pos);
+            CK(cudaMemcpyAsync(out + pos + hb, ctx->payload.p + p0, p1 - p0, cudaMemcpyDeviceToHost, st));
+            pos += hb + (p1 - p0);
+        }
+        offsets[g.n_images] = pos;
+        CK(cudaStreamSynchronize(st));
+        return LLCOMP_OK;
+    }
+
+    CK(ctx->sym.reserve(g.n_samples()));
+    CK(ctx->scratch.reserve(cap + 64));
+    CK(ctx->slice_bytes.reserve(ns));
+    CK(ctx->gstate.reserve(ns * (uint64_t)kStateBytes));
+    CK(ctx->offsets.reserve(ns + n_groups));
+    begin_call(ctx);
+    struct Part { int first, count; uint64_t slice0; };
+    std::vector<Part> parts;
+    for (int k = 0, first = 0; k < n_groups; ++k) {
+        const int count = g.n_images / n_groups + (k < g.n_images % n_groups ? 1 : 0);
+        parts.push_back({first, count, (uint64_t)first * spi});
+        first += count;
+    }
+    const uint64_t img_bytes = g.image_samples(), img_cap = 2 * img_bytes + kScratchSlack * spi;
+    // offsets land in pinned memory: a copy to pageable memory would block the host until the group is coded
+    CK(ctx->h_qoff.reserve(ns + n_groups));
+    std::vector<uint64_t*> off(n_groups);
+    for (int k = 0; k < n_groups; ++k) {
+        const Part& pt = parts[k];
+        cudaStream_t st = ctx->group_stream[k];
+        Geom gg = g;
+        gg.n_images = pt.count;
+        uint8_t* d_px = ctx->pixels.p + (uint64_t)pt.first * img_bytes;
+        uint64_t* d_off = ctx->offsets.p + pt.slice0 + k;
+        CK(cudaMemcpyAsync(d_px, pixels + (uint64_t)pt.first * img_bytes, (uint64_t)pt.count * img_bytes,
+                           cudaMemcpyHostToDevice, st));
+        const int rc = encode_fused_on(ctx, d_px, gg, pt.first, true, ctx->payload.p + (uint64_t)pt.first * img_cap,
+                                       (uint64_t)pt.count * img_cap, d_off, st);
+        if (rc) return rc;
+        off[k] = ctx->h_qoff.p + pt.slice0 + k;
+        CK(cudaMemcpyAsync(off[k], d_off, ((uint64_t)pt.count * spi + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    }
     uint64_t pos = 0;
-    for (int k = 0; k < g.n_images; ++k) {
-        const uint64_t p0 = off[(uint64_t)k * spi], p1 = off[(uint64_t)(k + 1) * spi];
-        offsets[k] = pos;
-        if (pos + hb + (p1 - p0) > out_cap) return LLCOMP_ERR_OVERFLOW;
-        write_header(g, &off[(uint64_t)k * spi], out + pos);
-        CK(cudaMemcpyAsync(out + pos + hb, ctx->payload.p + p0, p1 - p0, cudaMemcpyDeviceToHost, st));
-        pos += hb + (p1 - p0);
+    int status = LLCOMP_OK;
+    for (int k = 0; k < n_groups; ++k) {
+        const Part& pt = parts[k];
+        cudaStream_t st = ctx->group_stream[k];
+        CK(cudaStreamSynchronize(st));                       // this group's offsets are on the host now
+        const uint8_t* d_pay = ctx->payload.p + (uint64_t)pt.first * img_cap;
+        for (int i = 0; i < pt.count && status == LLCOMP_OK; ++i) {
+            const uint64_t* o = &off[k][(uint64_t)i * spi];
+            const uint64_t p0 = o[0], p1 = o[spi];
+            offsets[pt.first + i] = pos;
+            if (p1 > (uint64_t)pt.count * img_cap || pos + hb + (p1 - p0) > out_cap) { status = LLCOMP_ERR_OVERFLOW; break; }
+            write_header(g, o, out + pos);
+            CK(cudaMemcpyAsync(out + pos + hb, d_pay + p0, p1 - p0, cudaMemcpyDeviceToHost, st));
+            pos += hb + (p1 - p0);
+        }
     }
     offsets[g.n_images] = pos;
-    CK(cudaStreamSynchronize(st));
-    return LLCOMP_OK;
+    for (int k = 0; k < n_groups; ++k) CK(cudaStreamSynchronize(ctx->group_stream[k]));
+    int dev = 0;
+    CK(cudaMemcpy(&dev, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (dev != 0) { CK(cudaMemset(ctx->d_status, 0, sizeof(int))); return dev; }
+    return status;
 }
 
 int llcomp_b200_encode(llcomp_ctx* ctx, const uint8_t* pixels, int width, int height, int channels, int tile_w,

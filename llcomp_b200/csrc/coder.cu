@@ -598,7 +598,7 @@ cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8
                                      int* d_status, uint8_t* d_gstate, cudaStream_t st) {
     const uint64_t ns = g.n_slices();
     if (ns == 0 || ns > 0x0FFFFFFFull) return cudaErrorInvalidValue;
-    if (fused_global_state_bytes(ns)) {
+    if (d_gstate) {                                          // the caller decides (fused_global_state_bytes)
         cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);      // all states start at 0
         if (e != cudaSuccess) return e;
         k_slice_coder_fused<true><<<(unsigned)ns, 128, kFusedSmemNoState, st>>>(d_sym, g, d_scratch, d_slice_bytes,
