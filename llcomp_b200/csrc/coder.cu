@@ -19,6 +19,7 @@
 // else in global memory behind L1.
 #include <cstdlib>
 
+#include <cstdio>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -54,31 +55,47 @@ struct FifoSink {
     __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { fifo[(base + pos) & (kFifo - 1)] = (uint16_t)w; }
 };
 
-// One step of the model pass: 32 consecutive samples, one per lane (rec = packed record of this lane's sample).
-// Returns the number of decisions the step produced.  llcomp.hpp:166-206 (binarisation), :440-443 (state).
-template <class Sink>
-__device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint2* state,
-                                                const uint32_t* tab2, int lane, Sink sink) {
+// One step of the model pass: 32 consecutive samples, one per lane (rec = packed record of this lane's sample),
+// in two halves so that a caller can run the first half of step i+1 (warp votes and the ~330-cycle match, none of
+// which touch the state rows) under the second half of step i.
+// llcomp.hpp:166-206 (binarisation), :440-443 (state).
+struct StepPlan {
+    uint32_t off;        // position of the lane's first decision within the step
+    uint32_t total;      // decisions of the step
+    uint32_t members;    // lanes with this lane's context (lanes without a sample: themselves)
+    uint32_t zero_mask;  // lanes whose residual is zero
+};
+
+__device__ __forceinline__ int residual_of(uint32_t rec) { return ((int)(rec << 21)) >> 21; }
+
+__device__ __forceinline__ StepPlan model_plan(uint32_t rec, bool valid, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t hash = rec >> 11;
-    const int d = ((int)(rec << 21)) >> 21;
-    const uint32_t a = (uint32_t)abs(d);
+    const uint32_t a = (uint32_t)abs(residual_of(rec));
     const int e = a ? 31 - __clz(a) : -1;                                 // -1 marks a zero residual
     const uint32_t nb = valid ? 2u * e + 3u : 0u;                         // 1 decision for zero, else 2e+3
-
+    StepPlan p;
     // exclusive scan of the decision counts (<= 19, five bit planes, no dependent shuffles)
-    uint32_t off = 0, total = 0;
+    p.off = 0; p.total = 0;
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
         const uint32_t m = __ballot_sync(kFull, (nb >> b) & 1u);
-        off += __popc(m & lt_mask) << b;
-        total += __popc(m) << b;
+        p.off += __popc(m & lt_mask) << b;
+        p.total += __popc(m) << b;
     }
-
     // lanes with the same context form a chain; its first lane carries the row through the members
+    p.members = __match_any_sync(kFull, valid ? rec >> 11 : (0x10000u | lane));
+    p.zero_mask = __ballot_sync(kFull, valid && a == 0);
+    return p;
+}
+
+template <class Sink>
+__device__ __forceinline__ uint32_t model_apply(uint32_t rec, bool valid, const StepPlan& plan, uint2* state,
+                                                const uint32_t* tab2, int lane, Sink sink) {
+    const uint32_t hash = rec >> 11;
+    const int d = residual_of(rec);
+    const uint32_t off = plan.off;
+    uint32_t members = plan.members;
     const bool mine = valid;
-    const uint32_t key = mine ? hash : (0x10000u | lane);
-    uint32_t members = __match_any_sync(kFull, key);
     const int head = __ffs(members) - 1;
     const bool leader = mine && head == lane;
     uint2 row = make_uint2(0, 0);
@@ -86,8 +103,7 @@ __device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint2*
     // Smooth content: every member of the chain has a zero residual (one decision, "is zero" = 1, sub-state 0) and
     // that sub-state sits in the saturated state 127 (MPS 1, next-if-MPS 127, llcomp.hpp:258).  Then every member
     // gets the same entry and the row does not change: no need to walk the chain member by member.
-    const uint32_t zero_mask = __ballot_sync(kFull, valid && a == 0);
-    const bool flat = leader && (members & ~zero_mask) == 0 && (row.x & 0xFFu) == 127u;
+    const bool flat = leader && (members & ~plan.zero_mask) == 0 && (row.x & 0xFFu) == 127u;
     if (__any_sync(kFull, flat)) {
         const bool flat_chain = __shfl_sync(kFull, flat, head);          // every lane takes part in the shuffle
         if (mine && flat_chain) sink.put(off, tab2[127 * 2 + 1]);
@@ -139,7 +155,14 @@ __device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint2*
         state[hash] = make_uint2(s0b | (s1b << 8) | (s2b << 16) | (s3b << 24),
                                      s4b | (s5b << 8) | (s6b << 16) | (s7b << 24));
     __syncwarp();
-    return total;
+    return plan.total;
+}
+
+template <class Sink>
+__device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint2* state,
+                                                const uint32_t* tab2, int lane, Sink sink) {
+    const StepPlan plan = model_plan(rec, valid, lane);
+    return model_apply(rec, valid, plan, state, tab2, lane, sink);
 }
 
 // Table of the model pass: [state*2 + bit] = queue entry | next_state << 16 (llcomp.hpp:252-281, :290-292).
@@ -226,6 +249,12 @@ __device__ __noinline__ ByteTail renorm_slow(ByteTail t) {
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t prmt2(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
 
@@ -586,6 +615,342 @@ __global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __res
     }
 }
 
+// One decision of the range recurrence.  With x = range * M + A (24 bits),
+//   range' = x < 0x10000 ? x & ~0xFF : x >> 8   (RangeEncoder::put + the renormalisation shift, llcomp.hpp:57-73)
+// is (x >> 8) * f with f = 256 or 1, so x' = (x >> 8) * (M * f) + A.  The chain carries y = x + kChainBias, whose
+// bit 24 is [x >= 0x10000]: the selection of f is then arithmetic, three dependent operations per decision
+// (shift, multiply-add, multiply-add).  A compare feeding a select costs ~13 cycles of predicate latency, and
+// this recurrence is the critical path of the whole coder.  The A operand arrives with the bias already added.
+constexpr uint32_t kChainBias = 0xFF0000u;
+__device__ __forceinline__ uint32_t chain_step(uint32_t y, uint32_t m, uint32_t a_biased) {
+    const uint32_t nz = y >> 24;                             // 1: no renormalisation
+    const uint32_t a = (y >> 8) - (kChainBias >> 8);         // x >> 8
+    const uint32_t m256 = m << 8, nm255 = m * 0xFFFFFF01u;   // 256 M, -255 M
+    const uint32_t mf = nz * nm255 + m256;                   // M f
+    return a * mf + a_biased;
+}
+
+// Byte side of one block of the fused coder, lane-serial: lane l owns decisions [16 l, 16 l + 16) of the block,
+// so the low increments and the renormalisation flags are found without any cross-lane traffic; only the
+// renormalisations themselves (about one per ten decisions) are then compacted and handled one per lane.
+//   xr      x values of the block from the chain; the lane's own 16 words are reused as its event staging
+//   evl     scratch for the compacted event list (kBlkF + 3 words; aliases the consumed operand ring)
+//   nodelta bit 15 - i/2 (i even) / 31 - i/2 (i odd) set <=> decision 16 l + i codes a 0 (no low increment)
+// Same arithmetic as byte_side_block: exact re-statement of the low/carry half of RangeEncoder::put +
+// renorm_encoder (llcomp.hpp:38-73).
+__device__ __forceinline__ void byte_side_block16(ByteTail& t, bool& overflow, uint32_t& x_carry, uint32_t* xr,
+                                                  uint32_t* evl, uint32_t nodelta, uint32_t cnt, int lane,
+                                                  uint8_t* out0, uint8_t* out_end) {
+    uint32_t x[16];
+    {
+        const uint4* xv = reinterpret_cast<const uint4*>(xr + 16 * lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 v = xv[k];
+            x[4 * k] = v.x - kChainBias; x[4 * k + 1] = v.y - kChainBias;      // the chain stores x + kChainBias
+            x[4 * k + 2] = v.z - kChainBias; x[4 * k + 3] = v.w - kChainBias;
+        }
+    }
+    if (cnt < (uint32_t)kBlkF) {                              // last block of a slice: the rest is inert
+        const int mine = (int)cnt - 16 * lane;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i >= mine) { x[i] = 0x01000000u; nodelta |= 1u << ((i & 1) ? 31 - i / 2 : 15 - i / 2); }
+    }
+    uint32_t xp = __shfl_up_sync(kFull, x[15], 1);
+    if (lane == 0) xp = x_carry;
+    x_carry = __shfl_sync(kFull, x[15], 31);
+    uint32_t r = xp < 0x10000u ? (xp & 0xFFFFFF00u) : (xp >> 8);   // range before the lane's first decision
+    uint32_t sum = 0;
+    uint32_t* stage = xr + 16 * lane;
+    uint32_t* sp = stage;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t sh = x[i] >> 8;
+        if (!(nodelta & (1u << ((i & 1) ? 31 - i / 2 : 15 - i / 2)))) sum += r - sh;
+        const bool ev = x[i] < 0x10000u;
+        r = ev ? (x[i] & 0xFFFFFF00u) : sh;
+        if (ev) *sp++ = sum;
+    }
+    const uint32_t k_mine = (uint32_t)(sp - stage);
+    uint32_t inc_s = sum, inc_k = k_mine;                    // inclusive scans over lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ys = __shfl_up_sync(kFull, inc_s, d), yk = __shfl_up_sync(kFull, inc_k, d);
+        if (lane >= d) { inc_s += ys; inc_k += yk; }
+    }
+    const uint32_t e_tot = t.low + __shfl_sync(kFull, inc_s, 31);  // low after the block if nothing renormalised
+    const uint32_t n_ev = __shfl_sync(kFull, inc_k, 31);
+    if (n_ev == 0) { t.low = e_tot; return; }
+    // E_j = low entering the block + all increments up to renormalisation j, in event order; E_-1..-3 = 0
+    {
+        const uint32_t off = t.low + inc_s - sum;
+        uint32_t* dst = evl + 3 + (inc_k - k_mine);
+        for (uint32_t k = 0; k < k_mine; ++k) dst[k] = stage[k] + off;
+        if (lane < 3) evl[lane] = 0;
+    }
+    __syncwarp();
+    uint32_t low_last = 0, e_last = 0;
+    for (uint32_t j0 = 0; j0 < n_ev; j0 += 32) {
+        const uint32_t nv = min(32u, n_ev - j0);
+        const bool valid = (uint32_t)lane < nv;
+        const uint32_t* e = evl + j0 + (valid ? lane : 0);
+        const uint32_t e0 = e[3], e1 = e[2], e2 = e[1], e3 = e[0];
+        // low at renormalisation j: the byte kept from j-1's segment, then j's own segment
+        const uint32_t low_j = (((e1 - e2) & 0xFFu) << 8) + (e0 - e1);
+        const uint32_t low_p = (((e2 - e3) & 0xFFu) << 8) + (e1 - e2);
+        if (t.outp + (t.hp >> 9) + 32 + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
+        const bool defers = valid && (low_j - 0xFF01u) < 0xFFu;
+        if (t.hp < kHpEmpty && !__any_sync(kFull, defers)) {
+            // plain regime (see byte_side_block): every renormalisation emits the byte latched by its
+            // predecessor plus its own carry
+            const uint32_t held = lane == 0 ? t.hp : (low_p >> 8) & 0xFFu;
+            if (valid) t.outp[lane] = (uint8_t)(held + (low_j >> 16));
+            t.outp += nv;
+            const uint32_t ll = __shfl_sync(kFull, low_j, nv - 1);
+            t.hp = (ll >> 8) & 0xFFu;
+        } else {
+            for (uint32_t i = 0; i < nv; ++i) {
+                t.low = __shfl_sync(kFull, low_j, i);
+                shift_low(t);
+            }
+        }
+        low_last = __shfl_sync(kFull, low_j, nv - 1);
+        e_last = __shfl_sync(kFull, e0, nv - 1);
+    }
+    t.low = ((low_last & 0xFFu) << 8) + (e_tot - e_last);     // decisions after the last renormalisation
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 fused, NS slices per CTA (state rows behind L1 only).  Same three roles, but ONE chain warp serves NS
+// slices in lock step, 32/NS lanes each: the four instructions per decision of the range recurrence are then
+// issued once for NS slices.  The kernel is issue-bound (profiles/r01_v7_ncu_encode_summary.json: 12.7
+// warp-instructions per decision with one slice per chain warp), so this is worth NS-fold on the chain's share.
+// Warps: 0 chain, 1..NS model of slice q, NS+1..2NS helper of slice q (rotated by the CTA index).
+// ---------------------------------------------------------------------------------------------------
+// Which warp of the CTA takes which role.  The recurrence warp is the critical path and its speed depends on what
+// else issues from its SM sub-partition (measured: 353M cycles alone, 455M next to a second chain, 540M next to
+// two), so roles are dealt by the sub-partition each warp actually sits on (%warpid & 3): the k-th CTA to arrive
+// on an SM puts its chain on sub-partition k & 3, its model warps (the other heavy role) on the following ones,
+// and the light helper warps wherever is left.
+__device__ uint32_t g_sm_arrivals[1024];                      // CTAs started per SM, never reset: only k & 3 matters
+
+template <int NS>
+__device__ __forceinline__ int assign_role(int wslot, int lane) {
+    constexpr int kWarps = 1 + 2 * NS;
+    __shared__ uint32_t s_part[kWarps];
+    __shared__ uint32_t s_ord;
+    uint32_t smid, wid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm("mov.u32 %0, %%warpid;" : "=r"(wid));
+    if (lane == 0) s_part[wslot] = wid & 3u;
+    if (threadIdx.x == 0) s_ord = atomicAdd(&g_sm_arrivals[smid & 1023u], 1u);
+    __syncthreads();
+    const uint32_t c = s_ord & 3u;
+    uint32_t free_mask = (1u << kWarps) - 1u;
+    auto take = [&](uint32_t part) -> int {                  // a free warp on that sub-partition, else any free warp
+        int pick = __ffs(free_mask) - 1;
+#pragma unroll
+        for (int w = kWarps - 1; w >= 0; --w)
+            if (((free_mask >> w) & 1u) && s_part[w] == (part & 3u)) pick = w;
+        free_mask &= ~(1u << pick);
+        return pick;
+    };
+    int role = 0;
+    if (take(c) == wslot) role = 0;
+    constexpr uint32_t kModelAt[4] = {NS == 1 ? 2u : 1u, 2u, 3u, 2u};
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if (take(c + kModelAt[k & 3]) == wslot) role = 1 + k;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if (take(c + 3u + k) == wslot) role = 1 + NS + k;
+    return role;
+}
+
+constexpr int kFusedPerSlice = kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4 + 32;
+
+template <int NS>
+__global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(const uint32_t* __restrict__ sym, Geom g,
+                                                                          uint8_t* __restrict__ scratch,
+                                                                          uint32_t* __restrict__ slice_bytes,
+                                                                          int* __restrict__ status,
+                                                                          uint2* __restrict__ gstate, uint32_t n_slices,
+                                                                          uint32_t) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kWarps = 1 + 2 * NS;
+    constexpr int L = 32 / NS;                                // chain lanes per slice
+    uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem);
+    auto slice_smem = [&](int q) { return smem + 1024 + q * kFusedPerSlice; };
+    auto fifo_of = [&](int q) { return reinterpret_cast<uint16_t*>(slice_smem(q)); };
+    auto in_of = [&](int q, int buf) { return reinterpret_cast<uint2*>(slice_smem(q) + kFifo * 2) + buf * (kBlkF + 4); };
+    auto x_of = [&](int q, int buf) {
+        return reinterpret_cast<uint32_t*>(slice_smem(q) + kFifo * 2 + 2 * (kBlkF + 4) * 8) + buf * kBlkF;
+    };
+    auto ctl_of = [&](int q) {
+        return reinterpret_cast<volatile unsigned long long*>(slice_smem(q) + kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4);
+    };
+
+    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+    const int role = assign_role<NS>(wslot, lane);            // 0 chain, 1..NS model, NS+1..2NS helper
+    const int q = role == 0 ? lane / L : (role - 1) % NS;     // slice (within the CTA) this warp / lane group serves
+    const uint32_t sidx = blockIdx.x * NS + q;
+    const bool live = sidx < n_slices;                        // surplus slices of the last CTA: nothing to do
+    const uint64_t s = live ? sidx : n_slices - 1;
+    const Slice sl = slice_of(g, s);
+    const uint32_t* in = sym + sl.sym_off;
+    const uint64_t n = live ? sl.n : 0;
+    uint2* state = gstate + (size_t)s * kContexts;
+    uint16_t* fifo = fifo_of(q);
+    volatile unsigned long long* ctl = ctl_of(q);
+
+    if (role == 0) fill_tab2(tab2, lane);
+    __syncthreads();
+
+    // ---- model warp state
+    uint64_t base = 0, produced = 0;
+    const bool is_model = role >= 1 && role <= NS, is_helper = role > NS;
+    // software pipeline over 32-sample steps: records two steps ahead, the plan (votes, match) and an L1 prefetch
+    // of the state rows one step ahead.  A working set of 8 slices x ~4000 live rows does not fit L1, and a row
+    // fetched from L2 in the middle of a step costs ~700 cycles of a warp that has nothing else to do.
+    uint32_t rec_cur = (is_model && lane < n) ? in[lane] : 0u;
+    uint32_t rec_next = (is_model && 32 + lane < n) ? in[32 + lane] : 0u;
+    StepPlan plan_cur = {0, 0, 0, 0};
+    if (is_model) plan_cur = model_plan(rec_cur, lane < n, lane);
+    auto produce_until = [&](uint64_t target, uint32_t for_iter) {
+        while (base < n && produced < target) {
+            const bool valid = base + lane < n, valid_next = base + 32 + lane < n;
+            const uint64_t k = base + 64 + lane;
+            const uint32_t rec_after = k < n ? in[k] : 0u;
+            if (valid_next) asm volatile("prefetch.global.L1 [%0];" ::"l"(state + (rec_next >> 11)));
+            const StepPlan plan_next = model_plan(rec_next, valid_next, lane);
+            produced += model_apply(rec_cur, valid, plan_cur, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
+            rec_cur = rec_next; rec_next = rec_after; plan_cur = plan_next;
+            base += 32;
+        }
+        if (lane == 0) { ctl[2 * (for_iter & 1)] = produced; ctl[2 * (for_iter & 1) + 1] = base >= n ? 1ull : 0ull; }
+        __syncwarp();
+    };
+    // ---- helper warp state
+    uint8_t* const out0 = scratch + scratch_off(sl, s);
+    uint8_t* const out_end = out0 + scratch_cap(sl);
+    ByteTail t;
+    t.low = 0; t.hp = kHpEmpty; t.outp = out0;               // llcomp.hpp:35
+    bool overflow = false;
+    uint32_t x_carry = 0xFF00u << 8;                         // pseudo-x whose successor range is the initial 0xFF00
+    // ---- chain state (per lane group)
+    uint32_t xc = (0xFF00u << 8) + kChainBias;               // biased pseudo-x whose successor range is 0xFF00
+
+    static_assert(kBlkF == 512, "one lane expands and byte-codes 16 decisions of a block");
+    uint32_t nd_prev = 0, nd_cur = 0;                        // helper: no-delta masks of blocks b-1 and b
+    // helper: FIFO entries of block blk -> (M, A) operands for the chain; returns the lane's no-delta mask
+    auto expand = [&](uint32_t blk) -> uint32_t {
+        uint2* ring = in_of(q, blk & 1);
+        uint32_t nd = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int at = lane * 16 + h * 8;
+            const uint4 e = *reinterpret_cast<const uint4*>(fifo + ((blk * kBlkF) & (kFifo - 1)) + at);
+            const uint32_t w[4] = {e.x, e.y, e.z, e.w};
+            uint4* dst = reinterpret_cast<uint4*>(ring + at);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // M, A + kChainBias (A = 0xFF where the entry's flag is set: sign-replicating byte select)
+                dst[k] = make_uint4(w[k] & 0xFFu, prmt2(w[k], 0x0000FF00u, 0x4549), prmt(w[k], 0x4442),
+                                    prmt2(w[k], 0x0000FF00u, 0x454B));
+                nd |= (w[k] & 0x80008000u) >> (h * 4 + k);
+            }
+        }
+        return nd;
+    };
+
+    if (is_model) produce_until(3 * kBlkF, 0);
+    __syncthreads();
+    if (is_helper) nd_cur = expand(0);
+    __syncthreads();
+
+#ifdef LLC_ROLE_TIMING
+    long long t_work = 0, t_all0 = clock64();
+#endif
+    for (uint32_t b = 0;; ++b) {
+#ifdef LLC_ROLE_TIMING
+        const long long t_in = clock64();
+#endif
+        // decisions of block k of slice qq that exist (<= 0: none); identical in every warp
+        auto block_count = [&](int qq, uint32_t k) -> int {
+            volatile unsigned long long* c = ctl_of(qq);
+            if (c[2 * (b & 1) + 1] == 0) return kBlkF;
+            const long long left = (long long)c[2 * (b & 1)] - (long long)k * kBlkF;
+            return left > kBlkF ? kBlkF : (int)left;
+        };
+        int max_cur = 0, max_prev = 0;
+#pragma unroll
+        for (int qq = 0; qq < NS; ++qq) {
+            max_cur = max(max_cur, block_count(qq, b));
+            if (b > 0) max_prev = max(max_prev, block_count(qq, b - 1));
+        }
+        if (max_cur <= 0 && max_prev <= 0) break;
+
+        if (role == 0) {
+            if (max_cur > 0) {
+                const uint4* inp = reinterpret_cast<const uint4*>(in_of(q, b & 1));
+                uint4* xo = reinterpret_cast<uint4*>(x_of(q, b & 1));
+                const uint32_t n4 = ((uint32_t)max_cur + 3) / 4;       // shorter slices compute garbage that is ignored
+                uint4 p0 = inp[0], p1 = inp[1];
+#pragma unroll 4
+                for (uint32_t v = n4; v > 0; --v) {
+                    inp += 2;
+                    const uint4 q0 = inp[0], q1 = inp[1];
+                    uint4 xs;
+                    xs.x = xc = chain_step(xc, p0.x, p0.y);
+                    xs.y = xc = chain_step(xc, p0.z, p0.w);
+                    xs.z = xc = chain_step(xc, p1.x, p1.y);
+                    xs.w = xc = chain_step(xc, p1.z, p1.w);
+                    *xo++ = xs;
+                    p0 = q0; p1 = q1;
+                }
+            }
+        } else if (is_model) {
+            produce_until((uint64_t)(b + 4) * kBlkF, b + 1);
+        } else {
+            const int cnt_prev = b > 0 ? block_count(q, b - 1) : 0;
+            const int cnt_next = block_count(q, b + 1);
+            if (cnt_prev > 0)
+                byte_side_block16(t, overflow, x_carry, x_of(q, (b - 1) & 1),
+                                  reinterpret_cast<uint32_t*>(in_of(q, (b - 1) & 1)), nd_prev, (uint32_t)cnt_prev, lane,
+                                  out0, out_end);
+            nd_prev = nd_cur;
+            nd_cur = cnt_next > 0 ? expand(b + 1) : 0u;
+        }
+#ifdef LLC_ROLE_TIMING
+        t_work += clock64() - t_in;
+#endif
+        __syncthreads();
+    }
+#ifdef LLC_ROLE_TIMING
+    if (lane == 0) {
+        uint32_t smid;
+        uint32_t wid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm("mov.u32 %0, %%warpid;" : "=r"(wid));
+        printf("cta %d sm %u role %d work %lld total %lld wid %u\n", blockIdx.x, smid, role, t_work, clock64() - t_all0, wid);
+    }
+#endif
+
+    if (is_helper && live) {
+        if (t.outp + (t.hp >> 9) + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
+        // finish(), llcomp.hpp:75-81: range = 0xFF both times, so each renorm_encoder call shifts exactly once
+        t.low += 0xFFu;
+        shift_low(t);
+        shift_low(t);
+        if (lane == 0) {
+            slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(t.outp - out0);
+            if (overflow) atomicCAS(status, kDevOk, kDevOverflow);
+        }
+    }
+}
+
 constexpr int kFusedSmemNoState = 1024 + kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4 + 32;
 
 // The fused CTA with the state rows in shared memory takes 85 KB: 2 per SM.  Beyond 2 x 148 slices the rows go
@@ -601,8 +966,18 @@ cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8
     if (d_gstate) {                                          // the caller decides (fused_global_state_bytes)
         cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);      // all states start at 0
         if (e != cudaSuccess) return e;
-        k_slice_coder_fused<true><<<(unsigned)ns, 128, kFusedSmemNoState, st>>>(d_sym, g, d_scratch, d_slice_bytes,
-                                                                                 d_status, reinterpret_cast<uint2*>(d_gstate));
+        int per_cta = 2;                                     // slices per chain warp
+        if (const char* v = getenv("LLCOMP_FUSED_NS")) per_cta = atoi(v);
+        uint2* gs = reinterpret_cast<uint2*>(d_gstate);
+        const unsigned n = (unsigned)ns;
+        if (per_cta == 2)
+            k_slice_coder_fused_ns<2><<<(n + 1) / 2, 32 * 5, 1024 + 2 * kFusedPerSlice, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, 0u);
+        else if (per_cta == 11)
+            k_slice_coder_fused_ns<1><<<n, 32 * 3, 1024 + kFusedPerSlice, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, 0u);
+        else if (per_cta == 4)
+            k_slice_coder_fused_ns<4><<<(n + 3) / 4, 32 * 9, 1024 + 4 * kFusedPerSlice, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, 0u);
+        else
+            k_slice_coder_fused<true><<<n, 128, kFusedSmemNoState, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs);
     } else {
         k_slice_coder_fused<false><<<(unsigned)ns, 128, kFusedSmemNoState + kRowBytesSmem, st>>>(
             d_sym, g, d_scratch, d_slice_bytes, d_status, nullptr);
@@ -615,6 +990,14 @@ cudaError_t configure_slice_coder() {
     cudaError_t e = cudaFuncSetAttribute(k_model_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModelSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    kFusedSmemNoState + kRowBytesSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused_ns<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   1024 + 4 * kFusedPerSlice);
+    if (const char* v = getenv("LLCOMP_FUSED_CARVEOUT")) {   // experiment knob: shared-memory share of the L1 array, %
+        const int pct = atoi(v);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused_ns<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused_ns<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     return e;
 }
 
