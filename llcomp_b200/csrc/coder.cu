@@ -11,15 +11,15 @@
 // and (b) itself splits into the range recurrence (serial, 4 instructions per decision) and the low/carry/byte
 // side, which is a sum of per-decision increments between renormalisations and runs lane-parallel.
 //
-//   k_slice_coder_fused   default.  One CTA per slice, three warps: model (a), range chain, bytes; the warps hand
-//                         256..512-decision blocks to each other through shared memory.
+//   k_slice_coder_fused   default.  Warp roles: model (a), range chain, bytes; the warps hand 256-decision blocks
+//                         to each other through shared memory; one chain warp serves up to four slices.
 //   k_model_pass + k_range_pass_ws   the same work as two kernels with a 2-byte-per-decision queue in HBM
 //                         between them (LLCOMP_CODER_SPLIT=1; kept as a cross-check of the fused kernel).
 // The slice's 63,408 bytes of state rows live in shared memory while every slice of the launch finds a slot,
 // else in global memory behind L1.
+#include <cstdio>
 #include <cstdlib>
 
-#include <cstdio>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -48,12 +48,6 @@ struct QueueSink {
     uint16_t* q;
     __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { q[pos] = (uint16_t)w; }
 };
-constexpr int kFifo = 4096;                                  // entries; a multiple of the decision block
-struct FifoSink {
-    uint16_t* fifo;
-    uint32_t base;
-    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { fifo[(base + pos) & (kFifo - 1)] = (uint16_t)w; }
-};
 
 // One step of the model pass: 32 consecutive samples, one per lane (rec = packed record of this lane's sample),
 // in two halves so that a caller can run the first half of step i+1 (warp votes and the ~330-cycle match, none of
@@ -75,21 +69,29 @@ __device__ __forceinline__ StepPlan model_plan(uint32_t rec, bool valid, int lan
     const uint32_t nb = valid ? 2u * e + 3u : 0u;                         // 1 decision for zero, else 2e+3
     StepPlan p;
     // exclusive scan of the decision counts (<= 19, five bit planes, no dependent shuffles)
-    p.off = 0; p.total = 0;
+    p.off = 0;
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
         const uint32_t m = __ballot_sync(kFull, (nb >> b) & 1u);
         p.off += __popc(m & lt_mask) << b;
-        p.total += __popc(m) << b;
     }
+    p.total = __shfl_sync(kFull, p.off + nb, 31);
     // lanes with the same context form a chain; its first lane carries the row through the members
     p.members = __match_any_sync(kFull, valid ? rec >> 11 : (0x10000u | lane));
     p.zero_mask = __ballot_sync(kFull, valid && a == 0);
     return p;
 }
 
+// The row of the lane's context, fetched by the first lane of every chain (zero elsewhere).
+__device__ __forceinline__ uint2 model_row(uint32_t rec, bool valid, const StepPlan& plan, const uint2* state, int lane) {
+    const bool leader = valid && __ffs(plan.members) - 1 == lane;
+    uint2 row = make_uint2(0, 0);
+    if (leader) row = state[rec >> 11];
+    return row;
+}
+
 template <class Sink>
-__device__ __forceinline__ uint32_t model_apply(uint32_t rec, bool valid, const StepPlan& plan, uint2* state,
+__device__ __forceinline__ uint32_t model_apply(uint32_t rec, bool valid, const StepPlan& plan, uint2 row, uint2* state,
                                                 const uint32_t* tab2, int lane, Sink sink) {
     const uint32_t hash = rec >> 11;
     const int d = residual_of(rec);
@@ -98,8 +100,6 @@ __device__ __forceinline__ uint32_t model_apply(uint32_t rec, bool valid, const 
     const bool mine = valid;
     const int head = __ffs(members) - 1;
     const bool leader = mine && head == lane;
-    uint2 row = make_uint2(0, 0);
-    if (leader) row = state[hash];
     // Smooth content: every member of the chain has a zero residual (one decision, "is zero" = 1, sub-state 0) and
     // that sub-state sits in the saturated state 127 (MPS 1, next-if-MPS 127, llcomp.hpp:258).  Then every member
     // gets the same entry and the row does not change: no need to walk the chain member by member.
@@ -162,7 +162,7 @@ template <class Sink>
 __device__ __forceinline__ uint32_t model_chunk(uint32_t rec, bool valid, uint2* state,
                                                 const uint32_t* tab2, int lane, Sink sink) {
     const StepPlan plan = model_plan(rec, valid, lane);
-    return model_apply(rec, valid, plan, state, tab2, lane, sink);
+    return model_apply(rec, valid, plan, model_row(rec, valid, plan, state, lane), state, tab2, lane, sink);
 }
 
 // Table of the model pass: [state*2 + bit] = queue entry | next_state << 16 (llcomp.hpp:252-281, :290-292).
@@ -271,7 +271,6 @@ __device__ __forceinline__ void shift_low(ByteTail& t) {
 }
 
 constexpr int kBlk = 256;                                    // decisions per block of the split range pass
-constexpr int kBlkF = 512;                                   // decisions per block of the fused coder
 
 // Byte side of one block of `cnt` decisions (helper warp, lane-parallel over 32 decisions at a time): x values
 // from the chain, A operands (0 <=> the decision is a 1) from the operand ring.  Exact re-statement of the
@@ -463,209 +462,88 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2 fused: records -> slice payload in ONE kernel, three warps per slice, no bin queue in HBM.
-//   model warp   the model pass above, its entries go to a shared-memory FIFO instead of HBM;
-//   chain warp   the range recurrence (4 instructions per decision), as in k_range_pass_ws;
-//   helper warp  expands FIFO entries to (M, A) operands for the chain and runs the lane-parallel byte side.
-// The three meet at one named barrier per 256-decision block.  Before the barrier that ends iteration i the
-// model warp has produced at least (i+3) blocks (or everything); in iteration b the helper expands block b+1,
-// the chain runs block b, the helper turns block b-1 into bytes.  With the state rows behind L1 (kGlobalState)
-// the CTA needs ~12 KB of shared memory, so every slice of a 1024-image batch is resident; with the rows in
-// shared memory (<= 3 slices per SM) it takes 75 KB.
+// K2 fused: records -> slice payload in ONE kernel, no bin queue in HBM.  NS slices per CTA, 1 + 2 NS warps:
+//   model warp   (one per slice) the model pass above, its entries go to a shared-memory FIFO instead of HBM;
+//   chain warp   (one per CTA) the range recurrence of all NS slices in lock step, 32/NS lanes each;
+//   helper warp  (one per slice) expands FIFO entries to operands for the chain and runs the byte side.
+// They meet at one barrier per 256-decision block.  Before the barrier that ends iteration i the model warp has
+// produced at least (i+3) blocks (or everything); in iteration b the helper expands block b+1, the chain runs
+// block b, the helper turns block b-1 into bytes.  With the state rows behind L1 (kGlobalState) a slice needs
+// ~14 KB of shared memory, so every slice of a 1024-image batch is resident at once; with the rows in shared
+// memory (NS = 1, few slices) the CTA takes 79 KB.
+//
+// Who is the bottleneck was measured with per-role cycle counters: the serial recurrence is,
+// at 13 cycles of dependent latency per decision.  Everything here is arranged to keep that warp lean:
+// operands arrive pre-multiplied, one 16-byte shared load per decision, and no predicates on the dependent path.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void trio_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
-
-template <bool kGlobalState>
-__global__ void __launch_bounds__(128) k_slice_coder_fused(const uint32_t* __restrict__ sym, Geom g,
-                                                          uint8_t* __restrict__ scratch,
-                                                          uint32_t* __restrict__ slice_bytes, int* __restrict__ status,
-                                                          uint2* __restrict__ gstate) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kRowBytes = kGlobalState ? 0 : kRowBytesSmem;
-    uint2* state = kGlobalState ? gstate + (size_t)blockIdx.x * kContexts : reinterpret_cast<uint2*>(smem);
-    uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem + kRowBytes);
-    uint16_t* fifo = reinterpret_cast<uint16_t*>(smem + kRowBytes + 1024);
-    uint2 (*in_ring)[kBlkF + 4] = reinterpret_cast<uint2 (*)[kBlkF + 4]>(smem + kRowBytes + 1024 + kFifo * 2);
-    uint32_t (*x_ring)[kBlkF] = reinterpret_cast<uint32_t (*)[kBlkF]>(smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlkF + 4) * 8);
-    volatile unsigned long long* ctl = reinterpret_cast<volatile unsigned long long*>(
-        smem + kRowBytes + 1024 + kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4);
-    // Control words, double buffered by iteration parity p: ctl[2p] = decisions produced so far,
-    // ctl[2p+1] = 1 once the model warp has seen every sample.  Written by the model warp before the barrier
-    // that opens iteration p, read by everybody right after it.
-
-    // Four warp slots, three used; the assignment rotates with the CTA index to spread the chain warps of the
-    // CTAs that share an SM over its four schedulers.
-    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
-    const int r0 = blockIdx.x & 3;
-    const int role = (wslot - r0) & 3;                       // 0 chain, 1 model, 2 helper, 3 unused
-    if (role == 3) return;
-
-    const uint64_t s = blockIdx.x;
-    const Slice sl = slice_of(g, s);
-    const uint32_t* in = sym + sl.sym_off;
-    const uint64_t n = sl.n;
-
-    if (role == 1) {
-        if (!kGlobalState)
-            for (int i = lane; i < kRowBytes / 16; i += 32) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-        fill_tab2(tab2, lane);
-        __syncwarp();
-    }
-
-    // ---- model warp state
-    uint64_t base = 0;
-    uint64_t produced = 0;                                   // decisions so far
-    uint32_t rec_next = (role == 1 && lane < n) ? in[lane] : 0u;
-    // model warp: run steps until `target` decisions exist, then publish the counters for iteration `for_iter`
-    auto produce_until = [&](uint64_t target, uint32_t for_iter) {
-        while (base < n && produced < target) {
-            const uint32_t rec = rec_next;
-            const bool valid = base + lane < n;
-            const uint64_t k = base + 32 + lane;
-            rec_next = k < n ? in[k] : 0u;
-            produced += model_chunk(rec, valid, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
-            base += 32;
-        }
-        if (lane == 0) { ctl[2 * (for_iter & 1)] = produced; ctl[2 * (for_iter & 1) + 1] = base >= n ? 1ull : 0ull; }
-        __syncwarp();
-    };
-    // ---- helper warp state
-    uint8_t* const out0 = scratch + scratch_off(sl, s);
-    uint8_t* const out_end = out0 + scratch_cap(sl);
-    ByteTail t;
-    t.low = 0; t.hp = kHpEmpty; t.outp = out0;               // llcomp.hpp:35
-    bool overflow = false;
-    uint32_t x_carry = 0xFF00u << 8;                         // pseudo-x whose successor range is the initial 0xFF00
-    // ---- chain warp state
-    uint32_t range = 0xFF00u;
-
-    auto expand = [&](uint32_t blk) {                        // helper: FIFO entries of block blk -> (M, A) operands
-#pragma unroll
-        for (int h = 0; h < kBlkF / 256; ++h) {              // 8 entries per lane and pass
-            const int at = h * 256 + lane * 8;
-            const uint4 e = *reinterpret_cast<const uint4*>(fifo + ((blk * kBlkF) & (kFifo - 1)) + at);
-            const uint32_t w[4] = {e.x, e.y, e.z, e.w};
-            uint4* dst = reinterpret_cast<uint4*>(&in_ring[blk & 1][at]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                dst[k] = make_uint4(w[k] & 0xFFu, prmt(w[k], 0x4449), prmt(w[k], 0x4442), prmt(w[k], 0x444B));
-        }
-    };
-
-    // prime: three blocks of decisions, block 0 expanded
-    if (role == 1) produce_until(3 * kBlkF, 0);
-    trio_sync();
-    if (role == 2) expand(0);
-    trio_sync();
-
-    for (uint32_t b = 0;; ++b) {
-        // every warp reads the same control words here (written before the barrier that just completed)
-        const unsigned long long prod = ctl[2 * (b & 1)];
-        const bool fin = ctl[2 * (b & 1) + 1] != 0;
-        // number of decisions of block k known to exist: 256 unless finished and it is the last, partial one
-        auto block_count = [&](uint32_t k) -> int {          // <= 0: the block does not exist
-            if (!fin) return kBlkF;
-            const long long left = (long long)prod - (long long)k * kBlkF;
-            return left > kBlkF ? kBlkF : (int)left;
-        };
-        const int cnt_prev = b > 0 ? block_count(b - 1) : 0;
-        const int cnt_cur = block_count(b);
-        const int cnt_next = block_count(b + 1);
-        if (cnt_cur <= 0 && cnt_prev <= 0) break;            // nothing left for anybody
-
-        if (role == 0) {
-            if (cnt_cur > 0) {
-                const uint4* inp = reinterpret_cast<const uint4*>(in_ring[b & 1]);
-                uint4* xo = reinterpret_cast<uint4*>(x_ring[b & 1]);
-                const uint32_t n4 = ((uint32_t)cnt_cur + 3) / 4;      // garbage beyond cnt is computed and ignored
-                uint4 p0 = inp[0], p1 = inp[1];
-#pragma unroll 4
-                for (uint32_t v = n4; v > 0; --v) {
-                    inp += 2;
-                    const uint4 q0 = inp[0], q1 = inp[1];
-                    uint4 xs;
-                    xs.x = range * p0.x + p0.y; range = xs.x < 0x10000u ? (xs.x & 0xFFFFFF00u) : (xs.x >> 8);
-                    xs.y = range * p0.z + p0.w; range = xs.y < 0x10000u ? (xs.y & 0xFFFFFF00u) : (xs.y >> 8);
-                    xs.z = range * p1.x + p1.y; range = xs.z < 0x10000u ? (xs.z & 0xFFFFFF00u) : (xs.z >> 8);
-                    xs.w = range * p1.z + p1.w; range = xs.w < 0x10000u ? (xs.w & 0xFFFFFF00u) : (xs.w >> 8);
-                    *xo++ = xs;
-                    p0 = q0; p1 = q1;
-                }
-            }
-        } else if (role == 1) {
-            produce_until((uint64_t)(b + 4) * kBlkF, b + 1);
-        } else {
-            if (cnt_prev > 0) byte_side_block(t, overflow, x_carry, x_ring[(b - 1) & 1], in_ring[(b - 1) & 1],
-                                              (uint32_t)cnt_prev, lane, out0, out_end);
-            if (cnt_next > 0) expand(b + 1);
-        }
-        trio_sync();
-    }
-
-    if (role == 2) {
-        if (t.outp + (t.hp >> 9) + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
-        // finish(), llcomp.hpp:75-81: range = 0xFF both times, so each renorm_encoder call shifts exactly once
-        t.low += 0xFFu;
-        shift_low(t);
-        shift_low(t);
-        if (lane == 0) {
-            slice_bytes[s] = overflow ? 0xFFFFFFFFu : (uint32_t)(t.outp - out0);
-            if (overflow) atomicCAS(status, kDevOk, kDevOverflow);
-        }
-    }
-}
+constexpr int kBlkF = 256;                                   // decisions per block of the fused coder
+constexpr int kPerLane = kBlkF / 32;                         // helper: consecutive decisions per lane
+constexpr int kFifoF = 2048;                                 // FIFO entries: 3 blocks ahead + one step (<= 608) fit
+static_assert(3 * kBlkF + 32 * 19 + kBlkF <= kFifoF, "the model warp must not overrun the block being expanded");
+struct FifoSink {
+    uint16_t* fifo;
+    uint32_t base;
+    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { fifo[(base + pos) & (kFifoF - 1)] = (uint16_t)w; }
+};
 
 // One decision of the range recurrence.  With x = range * M + A (24 bits),
 //   range' = x < 0x10000 ? x & ~0xFF : x >> 8   (RangeEncoder::put + the renormalisation shift, llcomp.hpp:57-73)
 // is (x >> 8) * f with f = 256 or 1, so x' = (x >> 8) * (M * f) + A.  The chain carries y = x + kChainBias, whose
 // bit 24 is [x >= 0x10000]: the selection of f is then arithmetic, three dependent operations per decision
 // (shift, multiply-add, multiply-add).  A compare feeding a select costs ~13 cycles of predicate latency, and
-// this recurrence is the critical path of the whole coder.  The A operand arrives with the bias already added.
+// this recurrence is the critical path of the whole coder.  Operand: (256 M, -255 M, A + kChainBias).
 constexpr uint32_t kChainBias = 0xFF0000u;
-__device__ __forceinline__ uint32_t chain_step(uint32_t y, uint32_t m, uint32_t a_biased) {
+__device__ __forceinline__ uint32_t chain_step(uint32_t y, const uint4& op) {
     const uint32_t nz = y >> 24;                             // 1: no renormalisation
     const uint32_t a = (y >> 8) - (kChainBias >> 8);         // x >> 8
-    const uint32_t m256 = m << 8, nm255 = m * 0xFFFFFF01u;   // 256 M, -255 M
-    const uint32_t mf = nz * nm255 + m256;                   // M f
-    return a * mf + a_biased;
+    const uint32_t mf = nz * op.y + op.x;                    // M f
+    return a * mf + op.z;
 }
 
-// Byte side of one block of the fused coder, lane-serial: lane l owns decisions [16 l, 16 l + 16) of the block,
+// Operand ring of one block: decision e sits in slot (e % 8) * 32 + e / 8, so that the helper lane that expands
+// decisions 8 l .. 8 l + 7 writes its j-th operand next to its neighbours' j-th operands (no bank conflicts);
+// the chain reads one slot per decision either way.
+constexpr int kRingSlots = kBlkF + 8;                        // + look-ahead of the chain's operand prefetch
+__device__ __forceinline__ int ring_slot(int e) { return (e & 7) * 32 + (e >> 3); }
+
+// Byte side of one block of the fused coder, lane-serial: lane l owns decisions [8 l, 8 l + 8) of the block,
 // so the low increments and the renormalisation flags are found without any cross-lane traffic; only the
 // renormalisations themselves (about one per ten decisions) are then compacted and handled one per lane.
-//   xr      x values of the block from the chain; the lane's own 16 words are reused as its event staging
+//   xr      biased x values of the block from the chain; the lane's own words are reused as its event staging
 //   evl     scratch for the compacted event list (kBlkF + 3 words; aliases the consumed operand ring)
-//   nodelta bit 15 - i/2 (i even) / 31 - i/2 (i odd) set <=> decision 16 l + i codes a 0 (no low increment)
+//   nodelta bit 15 - i/2 (i even) / 31 - i/2 (i odd) set <=> decision 8 l + i codes a 0 (no low increment)
 // Same arithmetic as byte_side_block: exact re-statement of the low/carry half of RangeEncoder::put +
-// renorm_encoder (llcomp.hpp:38-73).
-__device__ __forceinline__ void byte_side_block16(ByteTail& t, bool& overflow, uint32_t& x_carry, uint32_t* xr,
-                                                  uint32_t* evl, uint32_t nodelta, uint32_t cnt, int lane,
-                                                  uint8_t* out0, uint8_t* out_end) {
-    uint32_t x[16];
+// renorm_encoder (llcomp.hpp:38-73).  With E_j = low entering the block + all increments up to renormalisation j
+// (E_-1 = E_-2 = E_-3 = 0), low at renormalisation j is (((E_j-1 - E_j-2) & 0xFF) << 8) + E_j - E_j-1: low mod 256
+// only depends on the last segment.
+__device__ __forceinline__ void byte_side_lanes(ByteTail& t, bool& overflow, uint32_t& x_carry, uint32_t* xr,
+                                                uint32_t* evl, uint32_t nodelta, uint32_t cnt, int lane,
+                                                uint8_t* out0, uint8_t* out_end) {
+    uint32_t x[kPerLane];
     {
-        const uint4* xv = reinterpret_cast<const uint4*>(xr + 16 * lane);
+        const uint4* xv = reinterpret_cast<const uint4*>(xr + kPerLane * lane);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kPerLane / 4; ++k) {
             const uint4 v = xv[k];
             x[4 * k] = v.x - kChainBias; x[4 * k + 1] = v.y - kChainBias;      // the chain stores x + kChainBias
             x[4 * k + 2] = v.z - kChainBias; x[4 * k + 3] = v.w - kChainBias;
         }
     }
     if (cnt < (uint32_t)kBlkF) {                              // last block of a slice: the rest is inert
-        const int mine = (int)cnt - 16 * lane;
+        const int mine = (int)cnt - kPerLane * lane;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < kPerLane; ++i)
             if (i >= mine) { x[i] = 0x01000000u; nodelta |= 1u << ((i & 1) ? 31 - i / 2 : 15 - i / 2); }
     }
-    uint32_t xp = __shfl_up_sync(kFull, x[15], 1);
+    uint32_t xp = __shfl_up_sync(kFull, x[kPerLane - 1], 1);
     if (lane == 0) xp = x_carry;
-    x_carry = __shfl_sync(kFull, x[15], 31);
+    x_carry = __shfl_sync(kFull, x[kPerLane - 1], 31);
     uint32_t r = xp < 0x10000u ? (xp & 0xFFFFFF00u) : (xp >> 8);   // range before the lane's first decision
     uint32_t sum = 0;
-    uint32_t* stage = xr + 16 * lane;
+    uint32_t* stage = xr + kPerLane * lane;
     uint32_t* sp = stage;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < kPerLane; ++i) {
         const uint32_t sh = x[i] >> 8;
         if (!(nodelta & (1u << ((i & 1) ? 31 - i / 2 : 15 - i / 2)))) sum += r - sh;
         const bool ev = x[i] < 0x10000u;
@@ -682,7 +560,6 @@ __device__ __forceinline__ void byte_side_block16(ByteTail& t, bool& overflow, u
     const uint32_t e_tot = t.low + __shfl_sync(kFull, inc_s, 31);  // low after the block if nothing renormalised
     const uint32_t n_ev = __shfl_sync(kFull, inc_k, 31);
     if (n_ev == 0) { t.low = e_tot; return; }
-    // E_j = low entering the block + all increments up to renormalisation j, in event order; E_-1..-3 = 0
     {
         const uint32_t off = t.low + inc_s - sum;
         uint32_t* dst = evl + 3 + (inc_k - k_mine);
@@ -696,7 +573,6 @@ __device__ __forceinline__ void byte_side_block16(ByteTail& t, bool& overflow, u
         const bool valid = (uint32_t)lane < nv;
         const uint32_t* e = evl + j0 + (valid ? lane : 0);
         const uint32_t e0 = e[3], e1 = e[2], e2 = e[1], e3 = e[0];
-        // low at renormalisation j: the byte kept from j-1's segment, then j's own segment
         const uint32_t low_j = (((e1 - e2) & 0xFFu) << 8) + (e0 - e1);
         const uint32_t low_p = (((e2 - e3) & 0xFFu) << 8) + (e1 - e2);
         if (t.outp + (t.hp >> 9) + 32 + 8 > out_end) { overflow = true; t.outp = out0; t.hp &= 0x1FFu; }
@@ -722,13 +598,6 @@ __device__ __forceinline__ void byte_side_block16(ByteTail& t, bool& overflow, u
     __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------------
-// K2 fused, NS slices per CTA (state rows behind L1 only).  Same three roles, but ONE chain warp serves NS
-// slices in lock step, 32/NS lanes each: the four instructions per decision of the range recurrence are then
-// issued once for NS slices.  The kernel is issue-bound (profiles/r01_v7_ncu_encode_summary.json: 12.7
-// warp-instructions per decision with one slice per chain warp), so this is worth NS-fold on the chain's share.
-// Warps: 0 chain, 1..NS model of slice q, NS+1..2NS helper of slice q (rotated by the CTA index).
-// ---------------------------------------------------------------------------------------------------
 // Which warp of the CTA takes which role.  The recurrence warp is the critical path and its speed depends on what
 // else issues from its SM sub-partition (measured: 353M cycles alone, 455M next to a second chain, 540M next to
 // two), so roles are dealt by the sub-partition each warp actually sits on (%warpid & 3): the k-th CTA to arrive
@@ -769,27 +638,30 @@ __device__ __forceinline__ int assign_role(int wslot, int lane) {
     return role;
 }
 
-constexpr int kFusedPerSlice = kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4 + 32;
+constexpr int kFusedPerSlice = kFifoF * 2 + 2 * kRingSlots * 16 + 2 * kBlkF * 4 + 32;
+constexpr int fused_smem_bytes(int ns, bool global_state) {
+    return 1024 + ns * kFusedPerSlice + (global_state ? 0 : kRowBytesSmem);
+}
 
-template <int NS>
-__global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(const uint32_t* __restrict__ sym, Geom g,
-                                                                          uint8_t* __restrict__ scratch,
-                                                                          uint32_t* __restrict__ slice_bytes,
-                                                                          int* __restrict__ status,
-                                                                          uint2* __restrict__ gstate, uint32_t n_slices,
-                                                                          uint32_t) {
+template <int NS, bool kGlobalState>
+__global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const uint32_t* __restrict__ sym, Geom g,
+                                                                       uint8_t* __restrict__ scratch,
+                                                                       uint32_t* __restrict__ slice_bytes,
+                                                                       int* __restrict__ status,
+                                                                       uint2* __restrict__ gstate, uint32_t n_slices) {
+    static_assert(kGlobalState || NS == 1, "the state rows of one slice fill the shared memory of a CTA");
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kWarps = 1 + 2 * NS;
     constexpr int L = 32 / NS;                                // chain lanes per slice
     uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem);
     auto slice_smem = [&](int q) { return smem + 1024 + q * kFusedPerSlice; };
     auto fifo_of = [&](int q) { return reinterpret_cast<uint16_t*>(slice_smem(q)); };
-    auto in_of = [&](int q, int buf) { return reinterpret_cast<uint2*>(slice_smem(q) + kFifo * 2) + buf * (kBlkF + 4); };
+    auto ring_of = [&](int q, int buf) { return reinterpret_cast<uint4*>(slice_smem(q) + kFifoF * 2) + buf * kRingSlots; };
     auto x_of = [&](int q, int buf) {
-        return reinterpret_cast<uint32_t*>(slice_smem(q) + kFifo * 2 + 2 * (kBlkF + 4) * 8) + buf * kBlkF;
+        return reinterpret_cast<uint32_t*>(slice_smem(q) + kFifoF * 2 + 2 * kRingSlots * 16) + buf * kBlkF;
     };
     auto ctl_of = [&](int q) {
-        return reinterpret_cast<volatile unsigned long long*>(slice_smem(q) + kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4);
+        return reinterpret_cast<volatile unsigned long long*>(slice_smem(q) + kFifoF * 2 + 2 * kRingSlots * 16 +
+                                                              2 * kBlkF * 4);
     };
 
     const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
@@ -801,19 +673,22 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(cons
     const Slice sl = slice_of(g, s);
     const uint32_t* in = sym + sl.sym_off;
     const uint64_t n = live ? sl.n : 0;
-    uint2* state = gstate + (size_t)s * kContexts;
+    uint2* state = kGlobalState ? gstate + (size_t)s * kContexts
+                                : reinterpret_cast<uint2*>(smem + 1024 + NS * kFusedPerSlice);
     uint16_t* fifo = fifo_of(q);
     volatile unsigned long long* ctl = ctl_of(q);
 
     if (role == 0) fill_tab2(tab2, lane);
+    if (!kGlobalState)
+        for (int i = threadIdx.x; i < kRowBytesSmem / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(state)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
-    // ---- model warp state
-    uint64_t base = 0, produced = 0;
     const bool is_model = role >= 1 && role <= NS, is_helper = role > NS;
-    // software pipeline over 32-sample steps: records two steps ahead, the plan (votes, match) and an L1 prefetch
-    // of the state rows one step ahead.  A working set of 8 slices x ~4000 live rows does not fit L1, and a row
-    // fetched from L2 in the middle of a step costs ~700 cycles of a warp that has nothing else to do.
+    // ---- model warp: software pipeline over 32-sample steps.  Records two steps ahead; the plan (votes, match)
+    // and an L1 prefetch of the state rows one step ahead: a working set of 8 slices x ~4000 live rows does not
+    // fit L1, and a row fetched from L2 in the middle of a step costs ~700 cycles of a warp with nothing else to do.
+    uint64_t base = 0, produced = 0;
     uint32_t rec_cur = (is_model && lane < n) ? in[lane] : 0u;
     uint32_t rec_next = (is_model && 32 + lane < n) ? in[32 + lane] : 0u;
     StepPlan plan_cur = {0, 0, 0, 0};
@@ -823,47 +698,43 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(cons
             const bool valid = base + lane < n, valid_next = base + 32 + lane < n;
             const uint64_t k = base + 64 + lane;
             const uint32_t rec_after = k < n ? in[k] : 0u;
-            if (valid_next) asm volatile("prefetch.global.L1 [%0];" ::"l"(state + (rec_next >> 11)));
+            // this step's rows first: their latency (L1, often L2) runs under the votes and the match of the next step
+            const uint2 row = model_row(rec_cur, valid, plan_cur, state, lane);
+            if (kGlobalState && valid_next) asm volatile("prefetch.global.L1 [%0];" ::"l"(state + (rec_next >> 11)));
             const StepPlan plan_next = model_plan(rec_next, valid_next, lane);
-            produced += model_apply(rec_cur, valid, plan_cur, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
+            produced += model_apply(rec_cur, valid, plan_cur, row, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
             rec_cur = rec_next; rec_next = rec_after; plan_cur = plan_next;
             base += 32;
         }
         if (lane == 0) { ctl[2 * (for_iter & 1)] = produced; ctl[2 * (for_iter & 1) + 1] = base >= n ? 1ull : 0ull; }
         __syncwarp();
     };
-    // ---- helper warp state
+    // ---- helper warp
     uint8_t* const out0 = scratch + scratch_off(sl, s);
     uint8_t* const out_end = out0 + scratch_cap(sl);
     ByteTail t;
     t.low = 0; t.hp = kHpEmpty; t.outp = out0;               // llcomp.hpp:35
     bool overflow = false;
     uint32_t x_carry = 0xFF00u << 8;                         // pseudo-x whose successor range is the initial 0xFF00
-    // ---- chain state (per lane group)
-    uint32_t xc = (0xFF00u << 8) + kChainBias;               // biased pseudo-x whose successor range is 0xFF00
-
-    static_assert(kBlkF == 512, "one lane expands and byte-codes 16 decisions of a block");
-    uint32_t nd_prev = 0, nd_cur = 0;                        // helper: no-delta masks of blocks b-1 and b
-    // helper: FIFO entries of block blk -> (M, A) operands for the chain; returns the lane's no-delta mask
+    uint32_t nd_prev = 0, nd_cur = 0;                        // no-delta masks of blocks b-1 and b
+    // FIFO entries of block blk -> chain operands (256 M, -255 M, A + bias); returns the lane's no-delta mask
     auto expand = [&](uint32_t blk) -> uint32_t {
-        uint2* ring = in_of(q, blk & 1);
+        uint4* ring = ring_of(q, blk & 1) + lane;            // the lane's j-th decision goes to slot j * 32 + lane
+        const uint4 e = *reinterpret_cast<const uint4*>(fifo + ((blk * kBlkF) & (kFifoF - 1)) + lane * kPerLane);
+        const uint32_t w[4] = {e.x, e.y, e.z, e.w};
         uint32_t nd = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int at = lane * 16 + h * 8;
-            const uint4 e = *reinterpret_cast<const uint4*>(fifo + ((blk * kBlkF) & (kFifo - 1)) + at);
-            const uint32_t w[4] = {e.x, e.y, e.z, e.w};
-            uint4* dst = reinterpret_cast<uint4*>(ring + at);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // M, A + kChainBias (A = 0xFF where the entry's flag is set: sign-replicating byte select)
-                dst[k] = make_uint4(w[k] & 0xFFu, prmt2(w[k], 0x0000FF00u, 0x4549), prmt(w[k], 0x4442),
-                                    prmt2(w[k], 0x0000FF00u, 0x454B));
-                nd |= (w[k] & 0x80008000u) >> (h * 4 + k);
-            }
+        for (int k = 0; k < 4; ++k) {
+            // A = 0xFF where the entry's flag (bit 15) is set: sign-replicating byte select, bias from the 2nd source
+            const uint32_t m_lo = w[k] & 0xFFu, m_hi = prmt(w[k], 0x4442);
+            ring[(2 * k) * 32] = make_uint4(m_lo << 8, m_lo * 0xFFFFFF01u, prmt2(w[k], 0x0000FF00u, 0x4549), 0u);
+            ring[(2 * k + 1) * 32] = make_uint4(m_hi << 8, m_hi * 0xFFFFFF01u, prmt2(w[k], 0x0000FF00u, 0x454B), 0u);
+            nd |= (w[k] & 0x80008000u) >> k;
         }
         return nd;
     };
+    // ---- chain warp (per lane group)
+    uint32_t yc = (0xFF00u << 8) + kChainBias;               // biased pseudo-x whose successor range is 0xFF00
 
     if (is_model) produce_until(3 * kBlkF, 0);
     __syncthreads();
@@ -894,21 +765,28 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(cons
 
         if (role == 0) {
             if (max_cur > 0) {
-                const uint4* inp = reinterpret_cast<const uint4*>(in_of(q, b & 1));
+                // eight decisions per trip; slots e%8*32 + e/8.  Operands of the next four are in flight while four
+                // run.  Shorter slices of the CTA (and the tail of a last block) compute garbage nobody reads.
+                const uint4* rp = ring_of(q, b & 1);
                 uint4* xo = reinterpret_cast<uint4*>(x_of(q, b & 1));
-                const uint32_t n4 = ((uint32_t)max_cur + 3) / 4;       // shorter slices compute garbage that is ignored
-                uint4 p0 = inp[0], p1 = inp[1];
-#pragma unroll 4
-                for (uint32_t v = n4; v > 0; --v) {
-                    inp += 2;
-                    const uint4 q0 = inp[0], q1 = inp[1];
+                const int trips = (max_cur + 7) / 8;
+                uint4 a0 = rp[0], a1 = rp[32], a2 = rp[64], a3 = rp[96];
+                for (int v = 0; v < trips; ++v) {
+                    const uint4 b0 = rp[128], b1 = rp[160], b2 = rp[192], b3 = rp[224];
                     uint4 xs;
-                    xs.x = xc = chain_step(xc, p0.x, p0.y);
-                    xs.y = xc = chain_step(xc, p0.z, p0.w);
-                    xs.z = xc = chain_step(xc, p1.x, p1.y);
-                    xs.w = xc = chain_step(xc, p1.z, p1.w);
-                    *xo++ = xs;
-                    p0 = q0; p1 = q1;
+                    xs.x = yc = chain_step(yc, a0);
+                    xs.y = yc = chain_step(yc, a1);
+                    xs.z = yc = chain_step(yc, a2);
+                    xs.w = yc = chain_step(yc, a3);
+                    xo[0] = xs;
+                    ++rp;
+                    a0 = rp[0]; a1 = rp[32]; a2 = rp[64]; a3 = rp[96];
+                    xs.x = yc = chain_step(yc, b0);
+                    xs.y = yc = chain_step(yc, b1);
+                    xs.z = yc = chain_step(yc, b2);
+                    xs.w = yc = chain_step(yc, b3);
+                    xo[1] = xs;
+                    xo += 2;
                 }
             }
         } else if (is_model) {
@@ -917,9 +795,9 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(cons
             const int cnt_prev = b > 0 ? block_count(q, b - 1) : 0;
             const int cnt_next = block_count(q, b + 1);
             if (cnt_prev > 0)
-                byte_side_block16(t, overflow, x_carry, x_of(q, (b - 1) & 1),
-                                  reinterpret_cast<uint32_t*>(in_of(q, (b - 1) & 1)), nd_prev, (uint32_t)cnt_prev, lane,
-                                  out0, out_end);
+                byte_side_lanes(t, overflow, x_carry, x_of(q, (b - 1) & 1),
+                                reinterpret_cast<uint32_t*>(ring_of(q, (b - 1) & 1)), nd_prev, (uint32_t)cnt_prev, lane,
+                                out0, out_end);
             nd_prev = nd_cur;
             nd_cur = cnt_next > 0 ? expand(b + 1) : 0u;
         }
@@ -928,10 +806,9 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(cons
 #endif
         __syncthreads();
     }
-#ifdef LLC_ROLE_TIMING
+#ifdef LLC_ROLE_TIMING                                       // per-role busy cycles
     if (lane == 0) {
-        uint32_t smid;
-        uint32_t wid;
+        uint32_t smid, wid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         asm("mov.u32 %0, %%warpid;" : "=r"(wid));
         printf("cta %d sm %u role %d work %lld total %lld wid %u\n", blockIdx.x, smid, role, t_work, clock64() - t_all0, wid);
@@ -951,53 +828,44 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused_ns(cons
     }
 }
 
-constexpr int kFusedSmemNoState = 1024 + kFifo * 2 + 2 * (kBlkF + 4) * 8 + 2 * kBlkF * 4 + 32;
-
-// The fused CTA with the state rows in shared memory takes 85 KB: 2 per SM.  Beyond 2 x 148 slices the rows go
+// The fused CTA with the state rows in shared memory takes 79 KB: 2 per SM.  Beyond 2 x 148 slices the rows go
 // behind L1 so that the whole launch is resident at once.
 uint64_t fused_global_state_bytes(uint64_t n_slices) {
     return (n_slices > 2 * 148 && !getenv("LLCOMP_MODEL_SMEM_STATE")) ? n_slices * (uint64_t)kStateBytes : 0;
+}
+
+template <int NS, bool kGlobalState>
+static cudaError_t launch_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
+                                int* d_status, uint2* gs, unsigned n, cudaStream_t st) {
+    k_slice_coder_fused<NS, kGlobalState><<<(n + NS - 1) / NS, 32 * (1 + 2 * NS), fused_smem_bytes(NS, kGlobalState), st>>>(
+        d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                                      int* d_status, uint8_t* d_gstate, cudaStream_t st) {
     const uint64_t ns = g.n_slices();
     if (ns == 0 || ns > 0x0FFFFFFFull) return cudaErrorInvalidValue;
-    if (d_gstate) {                                          // the caller decides (fused_global_state_bytes)
-        cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);      // all states start at 0
-        if (e != cudaSuccess) return e;
-        int per_cta = 2;                                     // slices per chain warp
-        if (const char* v = getenv("LLCOMP_FUSED_NS")) per_cta = atoi(v);
-        uint2* gs = reinterpret_cast<uint2*>(d_gstate);
-        const unsigned n = (unsigned)ns;
-        if (per_cta == 2)
-            k_slice_coder_fused_ns<2><<<(n + 1) / 2, 32 * 5, 1024 + 2 * kFusedPerSlice, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, 0u);
-        else if (per_cta == 11)
-            k_slice_coder_fused_ns<1><<<n, 32 * 3, 1024 + kFusedPerSlice, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, 0u);
-        else if (per_cta == 4)
-            k_slice_coder_fused_ns<4><<<(n + 3) / 4, 32 * 9, 1024 + 4 * kFusedPerSlice, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, 0u);
-        else
-            k_slice_coder_fused<true><<<n, 128, kFusedSmemNoState, st>>>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs);
-    } else {
-        k_slice_coder_fused<false><<<(unsigned)ns, 128, kFusedSmemNoState + kRowBytesSmem, st>>>(
-            d_sym, g, d_scratch, d_slice_bytes, d_status, nullptr);
-    }
-    return cudaGetLastError();
+    const unsigned n = (unsigned)ns;
+    if (!d_gstate) return launch_fused<1, false>(d_sym, g, d_scratch, d_slice_bytes, d_status, nullptr, n, st);
+    // the caller decides where the rows live (fused_global_state_bytes); all states start at 0
+    cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);
+    if (e != cudaSuccess) return e;
+    int per_cta = 2;                                         // slices per chain warp (4: 2% slower on cfg4)
+    if (const char* v = getenv("LLCOMP_FUSED_NS")) per_cta = atoi(v);
+    uint2* gs = reinterpret_cast<uint2*>(d_gstate);
+    if (per_cta == 1) return launch_fused<1, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
+    if (per_cta == 4) return launch_fused<4, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
+    return launch_fused<2, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
 cudaError_t configure_slice_coder() {
     cudaError_t e = cudaFuncSetAttribute(k_model_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModelSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   kFusedSmemNoState + kRowBytesSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused_ns<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   1024 + 4 * kFusedPerSlice);
-    if (const char* v = getenv("LLCOMP_FUSED_CARVEOUT")) {   // experiment knob: shared-memory share of the L1 array, %
-        const int pct = atoi(v);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused_ns<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused_ns<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   fused_smem_bytes(1, false));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_slice_coder_fused<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   fused_smem_bytes(4, true));
     return e;
 }
 
