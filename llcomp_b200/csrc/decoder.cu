@@ -232,6 +232,9 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
     pos = 2;                                                             // ring[pos] is the next unread byte ...
     uint32_t nextb = ring[2];                                            // ... and lane 0 keeps it in a register
     bool bad = false;
+    // the last CT-1 rows the chain wrote back, newest first (store-to-load forwarding for the requested rows)
+    int fwd_hash1 = -1, fwd_hash2 = -1, fwd_hash3 = -1;
+    uint2 fwd_row1 = make_uint2(0, 0), fwd_row2 = fwd_row1, fwd_row3 = fwd_row1;
 
     const size_t pitch = (size_t)g.W * CT;
     uint8_t* out0 = pixels + (size_t)sl.img * g.H * pitch + (size_t)sl.y0 * pitch + (size_t)sl.x0 * CT;
@@ -252,10 +255,36 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
         }
         __syncwarp();
 
-        // ---- the chain, in chunks so that the ring can be topped up by the whole warp
+        // ---- the chain, in chunks so that the ring can be topped up by the whole warp.
+        // Software pipeline over pixels: as soon as plane i of pixel w is reconstructed, everything plane i of
+        // pixel w+1 needs that does not depend on the bitstream is prepared -- neighbours, context hash
+        // (llcomp.hpp:494-507), median prediction (:509) -- and its state row is requested.  The row then has the
+        // CT-1 samples in between to arrive (it comes from L1 or L2 when the rows live in global memory); if one
+        // of those samples updates the same row, the fresh copy is taken from registers instead (fwd_*).
+        // (Measured and dropped: requesting the table entries of all 8 sub-states ahead as well, and mask-based
+        // selections instead of compare + select in a decision.  One thread issued in order pays ~4.3 cycles per
+        // instruction whatever it is, and both variants add instructions: 1722 -> 1950 ms on configs[3].)
         int l[CT], L[CT], tl[CT];
 #pragma unroll
         for (int i = 0; i < CT; ++i) { l[i] = 128; L[i] = 128; tl[i] = 0; }
+        int nt[CT] = {}, nhash[CT] = {}, npred[CT] = {};
+        uint2 nrow[CT] = {};
+        auto prepare = [&](int i, int w) {                   // lane 0: plane i of pixel w, from l / L / tl as they stand
+            const int j = w * CT + i;
+            // neighbours: first row -> t = tl = l; first column -> l = L = tl = t
+            const int t = h > 0 ? (int)bufA[j] : l[i];
+            if (w == 0 && h > 0) { l[i] = t; L[i] = t; tl[i] = t; }
+            const int tli = h > 0 ? tl[i] : l[i];
+            nhash[i] = (int)bufB[j] + q11lut[max(-128, min(127, l[i] - tli)) + 128] + 605 * dq5(L[i] - l[i]);   // :501-507
+            const int lt = l[i] + t - tli;
+            npred[i] = max(min(l[i], lt), min(max(l[i], lt), t));                            // median, :509
+            nt[i] = t;
+            nrow[i] = state[abs(nhash[i])];
+        };
+        if (lane == 0 && !bad) {
+#pragma unroll
+            for (int i = 0; i < CT; ++i) prepare(i, 0);
+        }
         const int px_per_chunk = kChunkSamples / CT;
         for (int w0 = 0; w0 < sl.w; w0 += px_per_chunk) {
             refill();
@@ -264,27 +293,15 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
                 const int w1 = min(sl.w, w0 + px_per_chunk);
                 for (int w = w0; w < w1; ++w) {
                     const int j = w * CT;
-                    // Contexts of all planes of this pixel first: they depend on the previous pixels only, so
-                    // their arithmetic overlaps (llcomp.hpp:494-515); the decode below is the serial part.
-                    int tv[CT], hashv[CT], predv[CT];
 #pragma unroll
                     for (int i = 0; i < CT; ++i) {
-                        // neighbours: first row -> t = tl = l; first column -> l = L = tl = t
-                        const int t = h > 0 ? (int)bufA[j + i] : l[i];
-                        if (w == 0 && h > 0) { l[i] = t; L[i] = t; tl[i] = t; }
-                        const int tli = h > 0 ? tl[i] : l[i];
-                        hashv[i] = (int)bufB[j + i] + q11lut[max(-128, min(127, l[i] - tli)) + 128] +
-                                   605 * dq5(L[i] - l[i]);                                  // :501-507
-                        const int lt = l[i] + t - tli;
-                        predv[i] = max(min(l[i], lt), min(max(l[i], lt), t));              // median, :509
-                        tv[i] = t;
-                    }
-#pragma unroll
-                    for (int i = 0; i < CT; ++i) {
-                        const int t = tv[i], predict = predv[i];
-                        const bool neg = hashv[i] < 0;                                      // :511-515
-                        const int hash = abs(hashv[i]);
-                        uint2 row = state[hash];
+                        const int t = nt[i], predict = npred[i];
+                        const bool neg = nhash[i] < 0;                                      // :511-515
+                        const int hash = abs(nhash[i]);
+                        uint2 row = nrow[i];
+                        if (CT > 1 && hash == fwd_hash1) row = fwd_row1;                    // updated since requested
+                        else if (CT > 2 && hash == fwd_hash2) row = fwd_row2;
+                        else if (CT > 3 && hash == fwd_hash3) row = fwd_row3;
 
                         // Table entries of the sub-states a residual can touch once, fetched together so that
                         // their shared-memory latency overlaps (ctx 4 and 6 repeat: fetched when reached).
@@ -333,11 +350,15 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
                             diff = bin(e7, row.y, 3) ? -(int)value : (int)value;             // :242-245
                         }
                         state[hash] = row;
+                        if (CT > 3) { fwd_hash3 = fwd_hash2; fwd_row3 = fwd_row2; }
+                        if (CT > 2) { fwd_hash2 = fwd_hash1; fwd_row2 = fwd_row1; }
+                        fwd_hash1 = hash; fwd_row1 = row;
                         const int cur = (int16_t)(predict + (neg ? -diff : diff));           // :526-529
                         bufB[j + i] = (int16_t)cur;
                         L[i] = w == 0 ? cur : l[i];                                          // w == 1: L = l (:496)
                         l[i] = cur;
                         tl[i] = t;
+                        if (w + 1 < sl.w) prepare(i, w + 1);
                     }
                     if (bad) break;
                 }
