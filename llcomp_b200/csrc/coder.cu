@@ -478,8 +478,12 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
 // ---------------------------------------------------------------------------------------------------
 constexpr int kBlkF = 256;                                   // decisions per block of the fused coder
 constexpr int kPerLane = kBlkF / 32;                         // helper: consecutive decisions per lane
-constexpr int kFifoF = 2048;                                 // FIFO entries: 3 blocks ahead + one step (<= 608) fit
-static_assert(3 * kBlkF + 32 * 19 + kBlkF <= kFifoF, "the model warp must not overrun the block being expanded");
+#ifndef LLC_AHEAD
+#define LLC_AHEAD 3
+#endif
+constexpr int kAhead = LLC_AHEAD;                            // blocks the model warp runs ahead of the chain
+constexpr int kFifoF = kAhead <= 3 ? 2048 : 4096;            // FIFO entries: kAhead blocks + one step (<= 608) fit
+static_assert(kAhead * kBlkF + 32 * 19 + kBlkF <= kFifoF, "the model warp must not overrun the block being expanded");
 struct FifoSink {
     uint16_t* fifo;
     uint32_t base;
@@ -638,7 +642,7 @@ __device__ __forceinline__ int assign_role(int wslot, int lane) {
     return role;
 }
 
-constexpr int kFusedPerSlice = kFifoF * 2 + 2 * kRingSlots * 16 + 2 * kBlkF * 4 + 32;
+constexpr int kFusedPerSlice = kFifoF * 2 + 2 * kRingSlots * 16 + 2 * kBlkF * 4 + 32;   // + control words
 constexpr int fused_smem_bytes(int ns, bool global_state) {
     return 1024 + ns * kFusedPerSlice + (global_state ? 0 : kRowBytesSmem);
 }
@@ -659,9 +663,11 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
     auto x_of = [&](int q, int buf) {
         return reinterpret_cast<uint32_t*>(slice_smem(q) + kFifoF * 2 + 2 * kRingSlots * 16) + buf * kBlkF;
     };
+    // per slice, per iteration parity: decisions that exist from block b on, as the model warp knew before the
+    // barrier that started iteration b (kUnbounded while it has not reached the end of the slice)
+    constexpr int kUnbounded = 1 << 30;
     auto ctl_of = [&](int q) {
-        return reinterpret_cast<volatile unsigned long long*>(slice_smem(q) + kFifoF * 2 + 2 * kRingSlots * 16 +
-                                                              2 * kBlkF * 4);
+        return reinterpret_cast<volatile int*>(slice_smem(q) + kFifoF * 2 + 2 * kRingSlots * 16 + 2 * kBlkF * 4);
     };
 
     const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
     uint2* state = kGlobalState ? gstate + (size_t)s * kContexts
                                 : reinterpret_cast<uint2*>(smem + 1024 + NS * kFusedPerSlice);
     uint16_t* fifo = fifo_of(q);
-    volatile unsigned long long* ctl = ctl_of(q);
+    volatile int* ctl = ctl_of(q);
 
     if (role == 0) fill_tab2(tab2, lane);
     if (!kGlobalState)
@@ -706,7 +712,10 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
             rec_cur = rec_next; rec_next = rec_after; plan_cur = plan_next;
             base += 32;
         }
-        if (lane == 0) { ctl[2 * (for_iter & 1)] = produced; ctl[2 * (for_iter & 1) + 1] = base >= n ? 1ull : 0ull; }
+        if (lane == 0) {
+            const long long left = (long long)produced - (long long)for_iter * kBlkF;
+            ctl[for_iter & 1] = base < n ? kUnbounded : (int)max(-(long long)kUnbounded, min((long long)kUnbounded, left));
+        }
         __syncwarp();
     };
     // ---- helper warp
@@ -736,7 +745,7 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
     // ---- chain warp (per lane group)
     uint32_t yc = (0xFF00u << 8) + kChainBias;               // biased pseudo-x whose successor range is 0xFF00
 
-    if (is_model) produce_until(3 * kBlkF, 0);
+    if (is_model) produce_until(kAhead * kBlkF, 0);
     __syncthreads();
     if (is_helper) nd_cur = expand(0);
     __syncthreads();
@@ -749,19 +758,15 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
         const long long t_in = clock64();
 #endif
         // decisions of block k of slice qq that exist (<= 0: none); identical in every warp
-        auto block_count = [&](int qq, uint32_t k) -> int {
-            volatile unsigned long long* c = ctl_of(qq);
-            if (c[2 * (b & 1) + 1] == 0) return kBlkF;
-            const long long left = (long long)c[2 * (b & 1)] - (long long)k * kBlkF;
-            return left > kBlkF ? kBlkF : (int)left;
-        };
-        int max_cur = 0, max_prev = 0;
+        int max_left = -kUnbounded;                          // decisions from block b on, longest slice of the CTA
 #pragma unroll
-        for (int qq = 0; qq < NS; ++qq) {
-            max_cur = max(max_cur, block_count(qq, b));
-            if (b > 0) max_prev = max(max_prev, block_count(qq, b - 1));
-        }
-        if (max_cur <= 0 && max_prev <= 0) break;
+        for (int qq = 0; qq < NS; ++qq) max_left = max(max_left, ctl_of(qq)[b & 1]);
+        const int my_left = ctl[b & 1];                      // ... and of this warp's slice (model, helper)
+        auto block_count = [&](int rel) -> int {             // decisions of block b + rel of this warp's slice
+            return min(kBlkF, my_left - rel * kBlkF);
+        };
+        const int max_cur = min(kBlkF, max_left);
+        if (max_cur <= 0 && (b == 0 || max_left + kBlkF <= 0)) break;   // nothing in block b nor in block b-1
 
         if (role == 0) {
             if (max_cur > 0) {
@@ -790,10 +795,10 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
                 }
             }
         } else if (is_model) {
-            produce_until((uint64_t)(b + 4) * kBlkF, b + 1);
+            produce_until((uint64_t)(b + 1 + kAhead) * kBlkF, b + 1);
         } else {
-            const int cnt_prev = b > 0 ? block_count(q, b - 1) : 0;
-            const int cnt_next = block_count(q, b + 1);
+            const int cnt_prev = b > 0 ? block_count(-1) : 0;
+            const int cnt_next = block_count(1);
             if (cnt_prev > 0)
                 byte_side_lanes(t, overflow, x_carry, x_of(q, (b - 1) & 1),
                                 reinterpret_cast<uint32_t*>(ring_of(q, (b - 1) & 1)), nd_prev, (uint32_t)cnt_prev, lane,
@@ -834,6 +839,9 @@ uint64_t fused_global_state_bytes(uint64_t n_slices) {
     return (n_slices > 2 * 148 && !getenv("LLCOMP_MODEL_SMEM_STATE")) ? n_slices * (uint64_t)kStateBytes : 0;
 }
 
+// (Measured and dropped: asking for a smaller shared-memory carve-out so that the rows behind L1 get more of it.
+// The default carve-out leaves them a 35% L1 hit rate, but the model warp hides that behind its look-ahead and the
+// kernel time did not move, while co-resident launches of a pipelined batch got slower.)
 template <int NS, bool kGlobalState>
 static cudaError_t launch_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                                 int* d_status, uint2* gs, unsigned n, cudaStream_t st) {
@@ -851,12 +859,12 @@ cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8
     // the caller decides where the rows live (fused_global_state_bytes); all states start at 0
     cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);
     if (e != cudaSuccess) return e;
-    int per_cta = 2;                                         // slices per chain warp (4: 2% slower on cfg4)
+    int per_cta = 4;                                         // slices per chain warp (2: 1% slower on configs[3])
     if (const char* v = getenv("LLCOMP_FUSED_NS")) per_cta = atoi(v);
     uint2* gs = reinterpret_cast<uint2*>(d_gstate);
     if (per_cta == 1) return launch_fused<1, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-    if (per_cta == 4) return launch_fused<4, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-    return launch_fused<2, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
+    if (per_cta == 2) return launch_fused<2, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
+    return launch_fused<4, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -297,6 +297,38 @@ def test_many_slices_decode_with_state_behind_l1(codec):
     assert payload[int(off[k]):int(off[k + 1])].cpu().numpy().tobytes() == oracle.encode_tile(imgs[5], x0, y0, sw, sh)
 
 
+def test_fused_coder_variants_agree(codec):
+    """The fused coder serves 1, 2 or 4 slices per chain warp (LLCOMP_FUSED_NS) with the state rows behind L1, or one
+    slice per CTA with the rows in shared memory (LLCOMP_MODEL_SMEM_STATE): same bytes from all of them, with ragged
+    slices and a slice count (378) that leaves the last CTA of the 4-slice form half empty."""
+    import torch
+    imgs = np.stack([oracle.generate(200, 180, 3, 9, 4100 + k) for k in range(9)])
+    g = codec.geometry(200, 180, 3, 32, 32, 9)                       # 7 x 6 tiles (last column 8 wide, last row 20 high)
+    assert codec.slice_count(g) == 378
+    d_px = torch.from_numpy(imgs).cuda()
+    payload, offsets = codec.encode_device(d_px, g)
+    codec.finish()
+    n = int(offsets[-1])
+    for var, val in (("LLCOMP_FUSED_NS", "1"), ("LLCOMP_FUSED_NS", "2"), ("LLCOMP_FUSED_NS", "4"),
+                     ("LLCOMP_MODEL_SMEM_STATE", "1")):
+        os.environ[var] = val
+        try:
+            p2, o2 = codec.encode_device(d_px, g)
+            codec.finish()
+        finally:
+            del os.environ[var]
+        assert torch.equal(o2, offsets) and torch.equal(p2[:n], payload[:n]), (var, val)
+    off = offsets.cpu().numpy()
+    tiles = tiles_of(200, 180, 32, 32)
+    for img, t in ((0, 0), (3, 6), (8, 41), (5, 20)):                 # corners and an interior slice against the oracle
+        k = img * 42 + t
+        x0, y0, sw, sh = tiles[t]
+        assert payload[int(off[k]):int(off[k + 1])].cpu().numpy().tobytes() == oracle.encode_tile(imgs[img], x0, y0, sw, sh)
+    out = codec.decode_device(payload, offsets, g)
+    codec.finish()
+    assert torch.equal(out.view(imgs.shape), d_px)
+
+
 def test_alternate_kernels_agree(codec):
     """Every stage has a plain variant behind a switch (one-thread-per-pixel front end, plain decoder chain,
     two-kernel coder); all of them must produce the same bytes / pixels as the default kernels."""
