@@ -298,6 +298,20 @@ def main():
         e2e = {"value": world * raw / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": raw,
                "d2h_bytes_per_step": e2e_stream + 8 * (n_slices + 1), "ms_per_step": dt * 1e3,
                "api": "llcomp_b200_encode_batch (host pixels -> host streams)"}
+        # what the copies alone cost on this box (the pipelined encode cannot start its last group before the
+        # upload is through, and a slice then still needs its full serial coding time)
+        def copy_ms(dst, src):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            a.record()
+            dst.copy_(src, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b)
+        e2e["h2d_alone_ms"] = copy_ms(px, h_px)
+        k = min(e2e_stream, raw, payload.numel())
+        e2e["d2h_alone_ms"] = copy_ms(h_back.view(-1)[:k], payload[:k]) * (e2e_stream / k)
         dt = e2e_timed(lambda: codec.decode_batch_ptr(h_out.data_ptr(), h_off.data_ptr(), n_img, h_back.data_ptr(), raw))
         ok = ok and bool(torch.equal(h_back, h_px))
         dec_e2e = {"value": world * raw / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": e2e_stream + 8 * (n_slices + 1),
@@ -329,9 +343,9 @@ def main():
         kernels.append({"name": name, "ms": ms, "share_of_step": ms / step_ms, "algorithmic_bytes": alg[name],
                         "achieved_GBps": ach, "frac_of_hbm_peak": ach / peak})
     dom = max((k for k in kernels if k["name"] != "slice_decoder"), key=lambda k: k["ms"])
-    # DRAM bytes per launch from the ncu --set full capture of this exact workload (profiles/r01_v7_ncu_encode_summary.json:
+    # DRAM bytes per launch from the ncu --set full capture of this exact workload (profiles/r01_v8_ncu_encode_summary.json:
     # dram__bytes_read.sum + dram__bytes_write.sum); only quoted when the run IS that workload.
-    ncu_traffic = {"slice_coder": 13.677075e9 + 2.949559e9, "frontend": 3.221430e9 + 12.856723e9}
+    ncu_traffic = {"slice_coder": 13.667476e9 + 3.200741e9, "frontend": 3.223117e9 + 12.846218e9}
     is_profiled_workload = (n_img, W, H, C, args.tile, args.noise) == (1024, 1024, 1024, 3, 0, 4)
     for k in kernels:
         k["ncu_dram_bytes"] = ncu_traffic.get(k["name"]) if is_profiled_workload else None

@@ -232,9 +232,11 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
     pos = 2;                                                             // ring[pos] is the next unread byte ...
     uint32_t nextb = ring[2];                                            // ... and lane 0 keeps it in a register
     bool bad = false;
-    // the last CT-1 rows the chain wrote back, newest first (store-to-load forwarding for the requested rows)
-    int fwd_hash1 = -1, fwd_hash2 = -1, fwd_hash3 = -1;
-    uint2 fwd_row1 = make_uint2(0, 0), fwd_row2 = fwd_row1, fwd_row3 = fwd_row1;
+    // the row every plane wrote back last (store-to-load forwarding for the rows requested ahead)
+    int wr_hash[CT];
+    uint2 wr_row[CT];
+#pragma unroll
+    for (int i = 0; i < CT; ++i) { wr_hash[i] = -1; wr_row[i] = make_uint2(0, 0); }
 
     const size_t pitch = (size_t)g.W * CT;
     uint8_t* out0 = pixels + (size_t)sl.img * g.H * pitch + (size_t)sl.y0 * pitch + (size_t)sl.x0 * CT;
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
         // pixel w+1 needs that does not depend on the bitstream is prepared -- neighbours, context hash
         // (llcomp.hpp:494-507), median prediction (:509) -- and its state row is requested.  The row then has the
         // CT-1 samples in between to arrive (it comes from L1 or L2 when the rows live in global memory); if one
-        // of those samples updates the same row, the fresh copy is taken from registers instead (fwd_*).
+        // of those samples updates the same row, the fresh copy is taken from registers instead (wr_*).
         // (Measured and dropped: requesting the table entries of all 8 sub-states ahead as well, and mask-based
         // selections instead of compare + select in a decision.  One thread issued in order pays ~4.3 cycles per
         // instruction whatever it is, and both variants add instructions: 1722 -> 1950 ms on configs[3].)
@@ -299,9 +301,11 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
                         const bool neg = nhash[i] < 0;                                      // :511-515
                         const int hash = abs(nhash[i]);
                         uint2 row = nrow[i];
-                        if (CT > 1 && hash == fwd_hash1) row = fwd_row1;                    // updated since requested
-                        else if (CT > 2 && hash == fwd_hash2) row = fwd_row2;
-                        else if (CT > 3 && hash == fwd_hash3) row = fwd_row3;
+#pragma unroll
+                        for (int k = CT - 1; k >= 1; --k) {                                 // updated since requested?
+                            const int p = (i + CT - k) % CT;                                // k samples ago; newest last
+                            if (hash == wr_hash[p]) row = wr_row[p];
+                        }
 
                         // Table entries of the sub-states a residual can touch once, fetched together so that
                         // their shared-memory latency overlaps (ctx 4 and 6 repeat: fetched when reached).
@@ -350,9 +354,7 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
                             diff = bin(e7, row.y, 3) ? -(int)value : (int)value;             // :242-245
                         }
                         state[hash] = row;
-                        if (CT > 3) { fwd_hash3 = fwd_hash2; fwd_row3 = fwd_row2; }
-                        if (CT > 2) { fwd_hash2 = fwd_hash1; fwd_row2 = fwd_row1; }
-                        fwd_hash1 = hash; fwd_row1 = row;
+                        wr_hash[i] = hash; wr_row[i] = row;
                         const int cur = (int16_t)(predict + (neg ? -diff : diff));           // :526-529
                         bufB[j + i] = (int16_t)cur;
                         L[i] = w == 0 ? cur : l[i];                                          // w == 1: L = l (:496)
