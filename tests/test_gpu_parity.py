@@ -329,6 +329,28 @@ def test_fused_coder_variants_agree(codec):
     assert torch.equal(out.view(imgs.shape), d_px)
 
 
+@pytest.mark.parametrize("c", [1, 2, 4])
+def test_many_slices_other_channel_counts(codec, c):
+    """480 slices of 1-, 2- and 4-channel images, half of them flat: the state rows of both the fused coder and the
+    decoder live behind L1, and flat content makes consecutive samples share a context row, which is the case the
+    decoder's row forwarding (rows requested one pixel ahead, rewritten in between) exists for."""
+    import torch
+    imgs = np.stack([oracle.generate(128, 96, c, 0 if k % 2 else 6, 7000 + 10 * c + k) for k in range(10)])
+    g = codec.geometry(128, 96, c, 16, 16, 10)
+    assert codec.slice_count(g) == 480
+    d_px = torch.from_numpy(imgs).cuda()
+    payload, offsets = codec.encode_device(d_px, g)
+    out = codec.decode_device(payload, offsets, g)
+    codec.finish()
+    assert torch.equal(out.view(imgs.shape), d_px)
+    off = offsets.cpu().numpy()
+    tiles = tiles_of(128, 96, 16, 16)
+    for img, t in ((0, 0), (1, 47), (6, 13), (9, 30)):
+        k = img * 48 + t
+        x0, y0, sw, sh = tiles[t]
+        assert payload[int(off[k]):int(off[k + 1])].cpu().numpy().tobytes() == oracle.encode_tile(imgs[img], x0, y0, sw, sh)
+
+
 def test_alternate_kernels_agree(codec):
     """Every stage has a plain variant behind a switch (one-thread-per-pixel front end, plain decoder chain,
     two-kernel coder); all of them must produce the same bytes / pixels as the default kernels."""
