@@ -115,31 +115,29 @@ constexpr int kHaloL = 2, kHaloR = 1, kHaloT = 2;
 constexpr int kSmemW = kTileW + kHaloL + kHaloR;           // 67 pixels per staged row
 constexpr int kSmemH = kTileH + kHaloT;                    // 18 rows
 
+// Quantisers as byte tables over the whole range a difference of two staged plane values can take (planes lie in
+// [-255, 382] after the colour transform, so differences lie in [-637, 637]): no clamp, the bias sits in the
+// load's immediate offset, and the weight a term carries in the hash is applied by the multiply-add that sums it.
+constexpr int kQBias = 640;
 struct QuantLuts {
-    // [x + 128] for x in [-128,127]; entries premultiplied by the weight the term carries in the hash
-    int16_t a[256];   // q11(x)              (l - tl)
-    int16_t b[256];   // q11(x) * 11         (tl - t)
-    int16_t c[256];   // q11(x) * 121        (t - tr)
-    int16_t d[256];   // q5(x) * 605         (L - l)
-    int16_t e[256];   // q5(x) * 3025        (T - t)
+    int8_t q11[2 * kQBias];   // q11(x), x + kQBias
+    int8_t q5[2 * kQBias];    // q5(x)
 };
 constexpr QuantLuts make_quant_luts() {
     QuantLuts t{};
-    for (int i = 0; i < 256; ++i) {
-        const int x = i - 128, a = x < 0 ? -x : x;
+    for (int i = 0; i < 2 * kQBias; ++i) {
+        const int x = i - kQBias, a = x < 0 ? -x : x;
         const int m11 = (a >= 1) + (a >= 2) + (a >= 5) + (a >= 12) + (a >= 35), m5 = (a >= 1) + (a >= 4);
-        const int q11 = x < 0 ? -m11 : m11, q5 = x < 0 ? -m5 : m5;
-        t.a[i] = (int16_t)q11; t.b[i] = (int16_t)(q11 * 11); t.c[i] = (int16_t)(q11 * 121);
-        t.d[i] = (int16_t)(q5 * 605); t.e[i] = (int16_t)(q5 * 3025);
+        t.q11[i] = (int8_t)(x < 0 ? -m11 : m11);
+        t.q5[i] = (int8_t)(x < 0 ? -m5 : m5);
     }
     return t;
 }
 __constant__ QuantLuts c_quant_luts = make_quant_luts();
-
-__device__ __forceinline__ int lut_index(int x) { return max(0, min(255, x + 128)); }   // clamp to [-128,127], + 128
+static_assert(sizeof(QuantLuts) % 16 == 0 && sizeof(QuantLuts) / 16 <= 256, "copied by one uint4 per thread");
 
 template <int CT, bool kCount>
-__global__ void __launch_bounds__(256, 6) k_frontend_tiled(const uint8_t* __restrict__ pixels, Geom g,
+__global__ void __launch_bounds__(256, 5) k_frontend_tiled(const uint8_t* __restrict__ pixels, Geom g,
                                                         uint32_t* __restrict__ sym,
                                                         unsigned long long* __restrict__ slice_bins) {
     static_assert(CT == 3 || CT == 4, "staged pixels hold 3 or 4 planes");
@@ -160,17 +158,21 @@ __global__ void __launch_bounds__(256, 6) k_frontend_tiled(const uint8_t* __rest
     // (clamped copies are never used as neighbours of a valid in-slice pixel)
     // (all loads of a thread are issued before the first use: 3 rows x 3 columns, fully unrolled)
     {
-        uint8_t raw[3][3][4];
+        // 32-bit offsets inside the image (an image is at most 16384 x 16384 x 4 bytes): one add per staged pixel
+        uint32_t raw[3][3][4] = {};
+        uint32_t rowoff[3], coloff[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            rowoff[a] = (uint32_t)min(max(ry0 + warp + 8 * a - kHaloT, 0), g.H - 1) * (uint32_t)pitch;
+            coloff[a] = (uint32_t)min(max(rx0 + lane + 32 * a - kHaloL, 0), g.W - 1) * CT;
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const int sy = warp + 8 * a;
-            const int y = min(max(ry0 + sy - kHaloT, 0), g.H - 1);
-            const uint8_t* rowp = base + (size_t)y * pitch;
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
                 const int sx = lane + 32 * b;
-                const int x = min(max(rx0 + sx - kHaloL, 0), g.W - 1);
-                const uint8_t* p = rowp + x * CT;
+                const uint8_t* p = base + (rowoff[a] + coloff[b]);
                 if (sy < kSmemH && sx < kSmemW) {
 #pragma unroll
                     for (int c = 0; c < CT; ++c) raw[a][b][c] = p[c];
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(256, 6) k_frontend_tiled(const uint8_t* __rest
             for (int b = 0; b < 3; ++b) {
                 const int sx = lane + 32 * b;
                 if (sy < kSmemH && sx < kSmemW) {
-                    const int gg = raw[a][b][1];
+                    const int gg = (int)raw[a][b][1];
                     const int r = (int)raw[a][b][0] - gg, bb = (int)raw[a][b][2] - gg;
                     tile[sy][sx] = make_int4(r, gg + (bb + r) / 4, bb, CT == 4 ? (int)raw[a][b][3] : 0);
                 }
@@ -213,7 +215,9 @@ __global__ void __launch_bounds__(256, 6) k_frontend_tiled(const uint8_t* __rest
         const int y0 = y >= yb ? yb : ty_a * g.th;
         const int sh = min(g.th, g.H - y0);
         const int h = y - y0;
-        uint32_t* out = img_out + ((size_t)y0 * g.W + (size_t)x0 * sh) * CT + ((size_t)h * sw + w) * CT;
+        // record index inside the image in 32 bits (an image has at most 2^30 samples)
+        uint32_t* out = img_out + (((uint32_t)y0 * (uint32_t)g.W + (uint32_t)x0 * (uint32_t)sh) +
+                                   ((uint32_t)h * (uint32_t)sw + (uint32_t)w)) * (uint32_t)CT;
         const int sy = ly + kHaloT, sx = lx + kHaloL;
         const int4 pc = tile[sy][sx];
         int4 pl, pL, ptl, pt, ptr, pT;
@@ -237,9 +241,10 @@ __global__ void __launch_bounds__(256, 6) k_frontend_tiled(const uint8_t* __rest
         unsigned bins = 0;
 #pragma unroll
         for (int i = 0; i < CT; ++i) {
-            int hash = lut.a[lut_index(l[i] - tl[i])] + lut.b[lut_index(tl[i] - t[i])] +
-                       lut.c[lut_index(t[i] - tr[i])] + lut.d[lut_index(L[i] - l[i])] +
-                       lut.e[lut_index(T[i] - t[i])];                                   // :424-429
+            const int8_t* q11 = lut.q11 + kQBias;
+            const int8_t* q5 = lut.q5 + kQBias;
+            int hash = q11[l[i] - tl[i]] + 11 * q11[tl[i] - t[i]] + 121 * q11[t[i] - tr[i]] +
+                       605 * q5[L[i] - l[i]] + 3025 * q5[T[i] - t[i]];                  // :424-429
             int diff = cur[i] - median3(l[i], l[i] + t[i] - tl[i], t[i]);               // :430-431
             if (hash < 0) { hash = -hash; diff = -diff; }                               // :433-436
             out[i] = pack_symbol(hash, diff);
