@@ -343,9 +343,9 @@ def main():
         kernels.append({"name": name, "ms": ms, "share_of_step": ms / step_ms, "algorithmic_bytes": alg[name],
                         "achieved_GBps": ach, "frac_of_hbm_peak": ach / peak})
     dom = max((k for k in kernels if k["name"] != "slice_decoder"), key=lambda k: k["ms"])
-    # DRAM bytes per launch from the ncu --set full capture of this exact workload (profiles/r01_v8_ncu_encode_summary.json:
+    # DRAM bytes per launch from the ncu --set full capture of this exact workload (profiles/r01_v9_ncu_encode_summary.json:
     # dram__bytes_read.sum + dram__bytes_write.sum); only quoted when the run IS that workload.
-    ncu_traffic = {"slice_coder": 13.667476e9 + 3.200741e9, "frontend": 3.223117e9 + 12.846218e9}
+    ncu_traffic = {"slice_coder": 13.659265e9 + 3.194658e9, "frontend": 3.222452e9 + 12.827327e9}
     is_profiled_workload = (n_img, W, H, C, args.tile, args.noise) == (1024, 1024, 1024, 3, 0, 4)
     for k in kernels:
         k["ncu_dram_bytes"] = ncu_traffic.get(k["name"]) if is_profiled_workload else None
