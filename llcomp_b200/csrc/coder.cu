@@ -29,6 +29,17 @@ __constant__ ModelTables c_tables = make_tables();
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+// Shared memory through 32-bit shared-window addresses: a generic pointer that is bumped or indexed in a loop makes
+// the compiler carry 64-bit address arithmetic through the warp-serial loops of the fused coder.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
 // Bin-queue entry (u16): bits 0..7 = M, bit 15 = "the decision is a 0".  With P = P(bit=1)*256 of the context:
 //   bit 1: M = P,       A = 0     range' = (range*M + A) >> 8 = range*P >> 8                (llcomp.hpp:62,69)
 //   bit 0: M = 256 - P, A = 255   range' = range - (range*P >> 8) = ceil(range*(256-P)/256)   (llcomp.hpp:66)
@@ -485,9 +496,11 @@ constexpr int kAhead = LLC_AHEAD;                            // blocks the model
 constexpr int kFifoF = kAhead <= 3 ? 2048 : 4096;            // FIFO entries: kAhead blocks + one step (<= 608) fit
 static_assert(kAhead * kBlkF + 32 * 19 + kBlkF <= kFifoF, "the model warp must not overrun the block being expanded");
 struct FifoSink {
-    uint16_t* fifo;
+    uint32_t fifo_s;     // shared-window address of the FIFO
     uint32_t base;
-    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { fifo[(base + pos) & (kFifoF - 1)] = (uint16_t)w; }
+    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const {
+        sts16(fifo_s + (((base + pos) & (kFifoF - 1)) << 1), w);
+    }
 };
 
 // One decision of the range recurrence.  With x = range * M + A (24 bits),
@@ -544,17 +557,17 @@ __device__ __forceinline__ void byte_side_lanes(ByteTail& t, bool& overflow, uin
     x_carry = __shfl_sync(kFull, x[kPerLane - 1], 31);
     uint32_t r = xp < 0x10000u ? (xp & 0xFFFFFF00u) : (xp >> 8);   // range before the lane's first decision
     uint32_t sum = 0;
-    uint32_t* stage = xr + kPerLane * lane;
-    uint32_t* sp = stage;
+    const uint32_t stage_s = smem_addr(xr) + 4u * kPerLane * lane;
+    uint32_t sp = stage_s;
 #pragma unroll
     for (int i = 0; i < kPerLane; ++i) {
         const uint32_t sh = x[i] >> 8;
         if (!(nodelta & (1u << ((i & 1) ? 31 - i / 2 : 15 - i / 2)))) sum += r - sh;
         const bool ev = x[i] < 0x10000u;
         r = ev ? (x[i] & 0xFFFFFF00u) : sh;
-        if (ev) *sp++ = sum;
+        if (ev) { sts32(sp, sum); sp += 4; }
     }
-    const uint32_t k_mine = (uint32_t)(sp - stage);
+    const uint32_t k_mine = (sp - stage_s) >> 2;
     uint32_t inc_s = sum, inc_k = k_mine;                    // inclusive scans over lanes
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -566,8 +579,8 @@ __device__ __forceinline__ void byte_side_lanes(ByteTail& t, bool& overflow, uin
     if (n_ev == 0) { t.low = e_tot; return; }
     {
         const uint32_t off = t.low + inc_s - sum;
-        uint32_t* dst = evl + 3 + (inc_k - k_mine);
-        for (uint32_t k = 0; k < k_mine; ++k) dst[k] = stage[k] + off;
+        const uint32_t dst_s = smem_addr(evl) + 4u * (3 + (inc_k - k_mine));
+        for (uint32_t k = 0; k < k_mine; ++k) sts32(dst_s + 4 * k, lds32(stage_s + 4 * k) + off);
         if (lane < 3) evl[lane] = 0;
     }
     __syncwarp();
@@ -708,7 +721,7 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
             const uint2 row = model_row(rec_cur, valid, plan_cur, state, lane);
             if (kGlobalState && valid_next) asm volatile("prefetch.global.L1 [%0];" ::"l"(state + (rec_next >> 11)));
             const StepPlan plan_next = model_plan(rec_next, valid_next, lane);
-            produced += model_apply(rec_cur, valid, plan_cur, row, state, tab2, lane, FifoSink{fifo, (uint32_t)produced});
+            produced += model_apply(rec_cur, valid, plan_cur, row, state, tab2, lane, FifoSink{smem_addr(fifo), (uint32_t)produced});
             rec_cur = rec_next; rec_next = rec_after; plan_cur = plan_next;
             base += 32;
         }
