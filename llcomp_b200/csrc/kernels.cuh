@@ -18,7 +18,7 @@ uint64_t model_global_state_bytes(uint64_t count);
 cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, const unsigned long long* d_nbins,
                               const Geom& g, uint64_t s0, uint64_t count, uint8_t* d_scratch, uint32_t* d_slice_bytes,
                               int* d_status, cudaStream_t st);
-// K2 fused: records -> per-slice scratch payloads in one kernel (model, chain and helper warp per slice), no bin
+// K2 fused: records -> per-slice scratch payloads in one kernel (model / chain / helper warp roles), no bin
 //     queue in HBM.  d_gstate != nullptr: the state rows live there (n_slices x 63,408 B, zeroed by the launch);
 //     nullptr: in shared memory.  fused_global_state_bytes() says which one a stand-alone launch should use.
 cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
