@@ -1,7 +1,9 @@
 # Builds the product library (CUDA, sm_100a only), the host tools and the test-only oracle.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
+# EXTRA: e.g. -DLLC_ROLE_TIMING (per-role cycle counters of the fused coder, see scripts/role_stats.py)
+EXTRA ?=
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v $(EXTRA)
 SRC := $(wildcard llcomp_b200/csrc/*.cu)
 HDR := $(wildcard llcomp_b200/csrc/*.cuh) include/llcomp_b200.h
 LIB := llcomp_b200/lib/libllcomp_b200.so
