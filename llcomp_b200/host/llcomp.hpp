@@ -111,4 +111,30 @@ inline std::vector<std::vector<uint8_t>> compressBatch(const std::vector<uint8_t
     return out;
 }
 
+// Inverse: n complete streams of the same geometry (same header, same tile grid) -> n images in one call.
+inline std::vector<RawImage> decompressBatch(const std::vector<std::vector<uint8_t>>& streams,
+                                             const Options& opt = Options{}) {
+    std::vector<RawImage> out;
+    if (streams.empty()) return out;
+    int w = 0, h = 0, ch = 0, tw = 0, th = 0;
+    llcomp_ctx* c = detail::context(opt.device);
+    int rc = llcomp_b200_peek(streams[0].data(), streams[0].size(), &w, &h, &ch, &tw, &th);
+    if (rc != LLCOMP_OK) detail::raise(c, rc);
+    std::vector<uint8_t> cat;
+    std::vector<uint64_t> off(streams.size() + 1, 0);
+    for (size_t k = 0; k < streams.size(); ++k) off[k + 1] = off[k] + streams[k].size();
+    cat.reserve(off.back());
+    for (const auto& s : streams) cat.insert(cat.end(), s.begin(), s.end());
+    const size_t per_image = (size_t)w * h * ch;
+    std::vector<uint8_t> px(per_image * streams.size());
+    llcomp_geometry g{};
+    rc = llcomp_b200_decode_batch(c, cat.data(), off.data(), (int)streams.size(), px.data(), px.size(), &g);
+    if (rc != LLCOMP_OK) detail::raise(c, rc);
+    out.reserve(streams.size());
+    for (size_t k = 0; k < streams.size(); ++k)
+        out.push_back(RawImage{std::vector<uint8_t>(px.begin() + k * per_image, px.begin() + (k + 1) * per_image),
+                               (uint16_t)w, (uint16_t)h, (uint8_t)ch});
+    return out;
+}
+
 }  // namespace llcomp

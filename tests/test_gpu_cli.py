@@ -67,3 +67,27 @@ def test_tile_option_and_errors(tools, tmp_path):
         f.write(bytes([0x77, 3, 1, 0, 1, 0, 0]))
     r = subprocess.run([llcompd, bad], capture_output=True, text=True)
     assert r.returncode == 1 and "Error decompressing image: Invalid magic number" in r.stderr
+
+
+def test_many_files_are_coded_as_batches(tools, tmp_path):
+    """More than one file: runs of equally sized images go through one batch call; every stream is still the
+    reference's bytes for that image, and the decoder tool groups streams by header the same way."""
+    llcompc, llcompd = tools
+    imgs = [oracle.generate(96, 64, 3, 4, 10 + k) for k in range(5)] + [oracle.generate(50, 40, 3, 6, 77)] + \
+           [oracle.generate(96, 64, 3, 0, 31)]
+    srcs = []
+    for k, img in enumerate(imgs):
+        srcs.append(str(tmp_path / ("f%d.ppm" % k)))
+        write_pnm(srcs[-1], img)
+    assert subprocess.run([llcompc] + srcs).returncode == 0
+    for src, img in zip(srcs, imgs):
+        with open(src + ".llcomp", "rb") as f:
+            assert f.read() == oracle.compress(img), src
+    assert subprocess.run([llcompd] + [s + ".llcomp" for s in srcs]).returncode == 0
+    for src, img in zip(srcs, imgs):
+        assert (read_pnm_payload(src + ".llcomp.ppm", img.size) == img.reshape(-1)).all(), src
+    # tiled containers batch too
+    assert subprocess.run([llcompc] + srcs[:3] + ["--tile", "32x32"]).returncode == 0
+    assert subprocess.run([llcompd] + [s + ".llcomp" for s in srcs[:3]]).returncode == 0
+    for src, img in zip(srcs[:3], imgs[:3]):
+        assert (read_pnm_payload(src + ".llcomp.ppm", img.size) == img.reshape(-1)).all(), src
