@@ -55,7 +55,12 @@ typedef struct {
     int32_t n_images;
 } llcomp_geometry;
 
-typedef struct llcomp_ctx llcomp_ctx;   /* per-device context: scratch buffers, tables, last error */
+typedef struct llcomp_ctx llcomp_ctx;   /* per-device context: scratch buffers, tables, last error.
+                                          * Calls on one context are serialised by a lock inside it (the reference's
+                                          * functions are re-entrant, llcomp.hpp:358/:461; this keeps a shared context
+                                          * safe).  The device-resident calls are asynchronous: two of them in flight
+                                          * on different streams need two contexts. */
+typedef struct llcomp_multi llcomp_multi; /* several devices of one box, one context and one host thread per device */
 
 int llcomp_b200_abi_version(void);
 const char *llcomp_b200_status_string(int status);
@@ -90,6 +95,20 @@ int llcomp_b200_decode_batch(llcomp_ctx *ctx, const uint8_t *streams, const uint
                              uint8_t *pixels_out, uint64_t pixels_cap, llcomp_geometry *g_out);
 void llcomp_b200_free(void *p);
 
+/* ---- several GPUs of one box ---------------- */
+/* Slices share nothing, so the work is dealt to the devices in contiguous blocks with no exchange between them:
+ * a batch by images, a single image by bands of tile rows.  Output bytes and offsets are exactly those of the
+ * single-device calls above (one stream per image; a banded image is one container with the slice table of the
+ * whole image).  devices[] may name a device more than once. */
+int llcomp_b200_multi_create(const int *devices, int n_devices, llcomp_multi **multi);
+void llcomp_b200_multi_destroy(llcomp_multi *multi);
+int llcomp_b200_multi_device_count(const llcomp_multi *multi);
+llcomp_ctx *llcomp_b200_multi_ctx(llcomp_multi *multi, int k);   /* context of the k-th device (last_error, launch counts) */
+int llcomp_b200_multi_encode_batch(llcomp_multi *multi, const uint8_t *pixels, const llcomp_geometry *g,
+                                   uint8_t *out, uint64_t out_cap, uint64_t *offsets);
+int llcomp_b200_multi_decode_batch(llcomp_multi *multi, const uint8_t *streams, const uint64_t *offsets, int n_images,
+                                   uint8_t *pixels_out, uint64_t pixels_cap, llcomp_geometry *g_out);
+
 /* ---- device-resident entry points (inputs and outputs stay in HBM) ------- */
 /* Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream).  Errors raised on the
  * device (overflow, invalid exponent) are collected by llcomp_b200_finish.
@@ -122,6 +141,10 @@ uint64_t llcomp_b200_last_bin_count(const llcomp_ctx *ctx);
 /* Only for the two-kernel coder kept behind LLCOMP_CODER_SPLIT=1 (the default fused coder has no queue):
  * bytes of HBM its bin queue may take; default 40 % of the device.  Tests shrink it to force launch groups. */
 void llcomp_b200_set_queue_budget(llcomp_ctx *ctx, uint64_t bytes);
+/* Test switches (LLCOMP_FRONTEND_SIMPLE, LLCOMP_FRONTEND_TILED, LLCOMP_DECODER_SIMPLE, LLCOMP_CODER_SPLIT,
+ * LLCOMP_DECODER_SMEM_STATE, LLCOMP_MODEL_SMEM_STATE, LLCOMP_FUSED_NS) select the plain GPU variant of a stage.  They are
+ * read from the environment when a context is created; call this after changing them in a live process. */
+void llcomp_b200_reload_switches(void);
 /* Model table entry of state s: P(bit=1)*256 | next_if_mps<<8 | next_if_lps<<16 (llcomp.hpp:252-281). */
 uint32_t llcomp_b200_debug_table(int s);
 

@@ -5,8 +5,8 @@ Only what the path needs lives here:
   host/     C++ mirror of the reference interface (llcomp.hpp) and the llcompc / llcompd tools
   codec.py  Python mirror of the same interface, used by tests and bench.py
 """
-from .codec import (Codec, Geometry, LlcompError, RawImage, compressImage, decompressImage, default_codec, ext,
+from .codec import (Codec, Geometry, LlcompError, MultiCodec, RawImage, compressImage, decompressImage, default_codec, ext,
                     magic_revision, revision)
 
-__all__ = ["Codec", "Geometry", "LlcompError", "RawImage", "compressImage", "decompressImage", "default_codec",
+__all__ = ["Codec", "Geometry", "LlcompError", "MultiCodec", "RawImage", "compressImage", "decompressImage", "default_codec",
            "ext", "magic_revision", "revision"]

@@ -54,6 +54,13 @@ SIGNATURES = {
     "llcomp_b200_debug_table": (C.c_uint32, [C.c_int]),
     "llcomp_b200_set_queue_budget": (None, [_vp, C.c_uint64]),
     "llcomp_b200_last_bin_count": (C.c_uint64, [_vp]),
+    "llcomp_b200_reload_switches": (None, []),
+    "llcomp_b200_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "llcomp_b200_multi_destroy": (None, [_vp]),
+    "llcomp_b200_multi_device_count": (C.c_int, [_vp]),
+    "llcomp_b200_multi_ctx": (_vp, [_vp, C.c_int]),
+    "llcomp_b200_multi_encode_batch": (C.c_int, [_vp, _vp, C.POINTER(Geometry), _vp, C.c_uint64, _vp]),
+    "llcomp_b200_multi_decode_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_uint64, C.POINTER(Geometry)]),
 }
 
 _lib = None
@@ -66,7 +73,8 @@ def lib() -> C.CDLL:
             raise RuntimeError(
                 f"{LIB} is missing: build it with `python -m llcomp_b200.build` (nvcc, sm_100a). "
                 "llcomp_b200 has no CPU fallback.")
-        L = C.CDLL(LIB)
+        # LLCOMP_B200_LIB: another build of the same library (kernel variants under test), never a different back end
+        L = C.CDLL(os.environ.get("LLCOMP_B200_LIB") or LIB)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

@@ -140,7 +140,10 @@ class Codec:
         buf = np.ascontiguousarray(buffer, dtype=np.uint8)
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = off.size - 1
-        w, h, c, _, _ = self.peek(buf[int(off[0]):int(off[1])].tobytes()[:4096 * 5])
+        first = buf[int(off[0]):int(off[1])]                       # the whole first stream: a big slice table is part of it
+        v = [C.c_int() for _ in range(5)]
+        self._check(self._L.llcomp_b200_peek(first.ctypes.data, first.size, *[C.byref(x) for x in v]))
+        w, h, c = v[0].value, v[1].value, v[2].value
         if out is None:
             out = np.empty((n, h, w, c), dtype=np.uint8)
         g = Geometry()
@@ -207,6 +210,10 @@ class Codec:
     def launch_count(self) -> int:
         return int(self._L.llcomp_b200_launch_count(self._h))
 
+    def reload_switches(self):
+        """Re-read the LLCOMP_* test switches from the environment (they are sampled when a context is created)."""
+        self._L.llcomp_b200_reload_switches()
+
     def set_profiling(self, on: bool):
         self._L.llcomp_b200_set_profiling(self._h, int(on))
 
@@ -221,6 +228,92 @@ class Codec:
         ms = (C.c_float * _capi.N_STAGES)()
         self._check(self._L.llcomp_b200_stage_times(self._h, ms))
         return {self._L.llcomp_b200_stage_name(i).decode(): float(ms[i]) for i in range(_capi.N_STAGES)}
+
+
+class MultiCodec:
+    """Several GPUs of one box behind one call (llcomp_b200_multi_*): a batch is dealt to the devices image-wise, a
+    single tiled image by bands of tile rows; one context and one host thread per device, no exchange between the
+    devices.  Streams are byte-identical to a single-device Codec's."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._L = _capi.lib()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self._L.llcomp_b200_multi_create(devs, len(devices), C.byref(h))
+        if rc:
+            raise LlcompError(rc, "no usable CUDA device; llcomp_b200 has no CPU fallback")
+        self._h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.llcomp_b200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            detail = ""
+            if rc == _capi.ERR_CUDA:
+                detail = "; ".join(self._L.llcomp_b200_last_error(self._L.llcomp_b200_multi_ctx(self._h, k)).decode()
+                                   for k in range(len(self.devices)))
+            raise LlcompError(rc, detail)
+
+    def launch_count(self) -> int:
+        return sum(int(self._L.llcomp_b200_launch_count(self._L.llcomp_b200_multi_ctx(self._h, k)))
+                   for k in range(len(self.devices)))
+
+    def compress_batch(self, images: np.ndarray, tile_w: int = 0, tile_h: int = 0, out: Optional[np.ndarray] = None):
+        a = np.ascontiguousarray(images, dtype=np.uint8)
+        n, h, w, c = a.shape
+        g = Geometry(w, h, c, tile_w, tile_h, n)
+        if out is None:
+            out = np.empty(int(self._L.llcomp_b200_stream_bound(C.byref(g))), dtype=np.uint8)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        self._check(self._L.llcomp_b200_multi_encode_batch(self._h, a.ctypes.data, C.byref(g), out.ctypes.data, out.size,
+                                                           offsets.ctypes.data))
+        return out, offsets
+
+    def decompress_batch(self, buffer: np.ndarray, offsets: Sequence[int], out: Optional[np.ndarray] = None):
+        buf = np.ascontiguousarray(buffer, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = off.size - 1
+        v = [C.c_int() for _ in range(5)]
+        first = buf[int(off[0]):int(off[1])]
+        self._check(self._L.llcomp_b200_peek(first.ctypes.data, first.size, *[C.byref(x) for x in v]))
+        w, h, c = v[0].value, v[1].value, v[2].value
+        if out is None:
+            out = np.empty((n, h, w, c), dtype=np.uint8)
+        g = Geometry()
+        self._check(self._L.llcomp_b200_multi_decode_batch(self._h, buf.ctypes.data, off.ctypes.data, n, out.ctypes.data,
+                                                           out.size, C.byref(g)))
+        return out
+
+    def compress(self, rgb, width: int, height: int, channels: int, tile_w: int = 0, tile_h: int = 0) -> bytes:
+        """One image; with a tile grid of two or more tile rows the bands go to different devices."""
+        a = np.ascontiguousarray(np.asarray(rgb, dtype=np.uint8).reshape(1, height, width, channels))
+        out, off = self.compress_batch(a, tile_w, tile_h)
+        return out[:int(off[1])].tobytes()
+
+    def decompress(self, data: bytes) -> RawImage:
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        px = self.decompress_batch(buf, [0, buf.size])
+        _, h, w, c = px.shape
+        return RawImage(px[0], w, h, c)
+
+    def encode_batch_ptr(self, pixels_ptr: int, g: Geometry, out_ptr: int, out_cap: int, offsets_ptr: int):
+        self._check(self._L.llcomp_b200_multi_encode_batch(self._h, pixels_ptr, C.byref(g), out_ptr, out_cap, offsets_ptr))
+
+    def decode_batch_ptr(self, streams_ptr: int, offsets_ptr: int, n_images: int, out_ptr: int, out_cap: int):
+        g = Geometry()
+        self._check(self._L.llcomp_b200_multi_decode_batch(self._h, streams_ptr, offsets_ptr, n_images, out_ptr, out_cap,
+                                                           C.byref(g)))
+        return g
 
 
 _default: dict[int, Codec] = {}

@@ -3,10 +3,13 @@
 // (compressImage) and llcompd.cpp:26 (decompressImage) of the reference; header layout follows
 // llcomp.hpp:375-378 / :463-470.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -15,6 +18,23 @@
 #include "kernels.cuh"
 
 using namespace llc;
+
+namespace llc {
+static Switches g_switches;
+const Switches& switches() { return g_switches; }
+void reload_switches() {
+    auto on = [](const char* name) { const char* v = getenv(name); return v && *v && std::strcmp(v, "0") != 0; };
+    Switches s;
+    s.frontend_simple = on("LLCOMP_FRONTEND_SIMPLE");
+    s.frontend_tiled = on("LLCOMP_FRONTEND_TILED");
+    s.decoder_simple = on("LLCOMP_DECODER_SIMPLE");
+    s.coder_split = on("LLCOMP_CODER_SPLIT");
+    s.decoder_smem_state = on("LLCOMP_DECODER_SMEM_STATE");
+    s.model_smem_state = on("LLCOMP_MODEL_SMEM_STATE");
+    if (const char* v = getenv("LLCOMP_FUSED_NS")) s.fused_ns = atoi(v);
+    g_switches = s;
+}
+}  // namespace llc
 
 namespace {
 
@@ -55,6 +75,7 @@ struct DevBuf {
 }  // namespace
 
 struct llcomp_ctx {
+    std::recursive_mutex mu;                // one call at a time per context (the work buffers below are shared)
     int device = 0;
     cudaStream_t stream = nullptr;          // used by the host-buffer entry points
     static constexpr int kGroups = 4;       // host-buffer encode: image groups pipelined over this many streams
@@ -217,11 +238,108 @@ int encode_fused_on(llcomp_ctx* ctx, const uint8_t* d_pixels, const Geom& g, uin
     return LLCOMP_OK;
 }
 
+
+// ---- host-buffer decode ----------------------------------------------------------------------------
+// Headers of a batch of streams, parsed on the host: the slice table of the whole batch (offsets inside one contiguous
+// device payload) and, per image, which host bytes exist (a truncated stream reads as zero beyond its end,
+// llcomp.hpp:476-477).
+struct ParsedBatch {
+    llcomp_geometry gi{};
+    std::vector<uint64_t> off;          // n_slices + 1
+    struct Piece { uint64_t src, dst, have, want; };
+    std::vector<Piece> pieces;          // one per image
+};
+
+int parse_batch(const uint8_t* streams, const uint64_t* offsets, int n_images, ParsedBatch& pb) {
+    std::vector<uint32_t> lens;
+    uint64_t total = 0;
+    pb.off.assign(1, 0);
+    pb.pieces.clear();
+    for (int k = 0; k < n_images; ++k) {
+        const uint8_t* s = streams + offsets[k];
+        const size_t n = (size_t)(offsets[k + 1] - offsets[k]);
+        llcomp_geometry gk; size_t hdr;
+        const int rc = parse_header(s, n, &gk, &hdr, &lens);
+        if (rc) return rc;
+        if (k == 0) pb.gi = gk;
+        else if (gk.width != pb.gi.width || gk.height != pb.gi.height || gk.channels != pb.gi.channels ||
+                 gk.tile_w != pb.gi.tile_w || gk.tile_h != pb.gi.tile_h) return LLCOMP_ERR_BAD_ARG;
+        uint64_t want = 0;
+        for (uint32_t L : lens) { want += L; pb.off.push_back(total + want); }
+        pb.pieces.push_back({offsets[k] + hdr, total, std::min<uint64_t>(want, n - hdr), want});
+        total += want;
+    }
+    pb.gi.n_images = n_images;
+    return LLCOMP_OK;
+}
+
+// Decodes images [first, first + count) of a parsed batch into pixels_out (their pixels, back to back).  Image groups
+// are pipelined over a few streams: payload upload, slice decoder and pixel download of different groups overlap.
+int decode_parsed(llcomp_ctx* ctx, const uint8_t* streams, const ParsedBatch& pb, const Geom& g_all, int first, int count,
+                  uint8_t* pixels_out) {
+    CK(cudaSetDevice(ctx->device));
+    Geom g = g_all;
+    g.n_images = count;
+    const uint64_t spi = g.slices_per_image(), ns = g.n_slices(), img_bytes = g.image_samples();
+    const uint64_t s0 = (uint64_t)first * spi;
+    const uint64_t pay0 = pb.off[s0], pay_bytes = pb.off[s0 + ns] - pay0;
+    const int n_groups = count >= 2 * llcomp_ctx::kGroups ? llcomp_ctx::kGroups : 1;
+    const bool shared = n_groups > 1;
+    CK(ctx->payload.reserve(pay_bytes + 16));
+    CK(ctx->offsets.reserve(ns + n_groups));
+    CK(ctx->pixels.reserve(g.n_samples()));
+    const uint64_t lb = decoder_line_scratch_bytes(g);
+    if (lb) CK(ctx->lines.reserve(lb / 2));
+    const uint64_t gb = decoder_global_state_bytes(g, shared);
+    if (gb) CK(ctx->gstate.reserve(gb));
+    // offsets relative to this call's payload buffer, in pinned memory (uploads from pageable memory would serialise)
+    CK(ctx->h_qoff.reserve(ns + n_groups));
+    begin_call(ctx);
+    int img = 0;
+    for (int k = 0; k < n_groups; ++k) {
+        const int cnt = count / n_groups + (k < count % n_groups ? 1 : 0);
+        cudaStream_t st = n_groups == 1 ? ctx->stream : ctx->group_stream[k];
+        const uint64_t sl0 = (uint64_t)img * spi, nsl = (uint64_t)cnt * spi;
+        uint64_t* h_off = ctx->h_qoff.p + sl0 + k;
+        for (uint64_t i = 0; i <= nsl; ++i) h_off[i] = pb.off[s0 + sl0 + i] - pay0;
+        uint64_t* d_off = ctx->offsets.p + sl0 + k;
+        CK(cudaMemcpyAsync(d_off, h_off, (nsl + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < cnt; ++i) {
+            const ParsedBatch::Piece& pc = pb.pieces[first + img + i];
+            uint8_t* dst = ctx->payload.p + (pc.dst - pay0);
+            if (pc.have) CK(cudaMemcpyAsync(dst, streams + pc.src, pc.have, cudaMemcpyHostToDevice, st));
+            if (pc.have < pc.want) CK(cudaMemsetAsync(dst + pc.have, 0, pc.want - pc.have, st));
+        }
+        Geom gg = g;
+        gg.n_images = cnt;
+        uint8_t* d_px = ctx->pixels.p + (uint64_t)img * img_bytes;
+        int16_t* lines = lb ? ctx->lines.p + sl0 * (3ull * std::min(g.tw, g.W) * g.C) : nullptr;
+        uint8_t* gstate = gb ? ctx->gstate.p + sl0 * (uint64_t)kStateBytes : nullptr;
+        {
+            StageScope sc(ctx, st, kStDecoder);
+            CK(launch_slice_decoder(ctx->payload.p, d_off, gg, d_px, lines, gstate, ctx->d_status, st, shared));
+        }
+        CK(cudaMemcpyAsync(pixels_out + (uint64_t)img * img_bytes, d_px, (uint64_t)cnt * img_bytes, cudaMemcpyDeviceToHost, st));
+        img += cnt;
+    }
+    cudaError_t first_err = cudaSuccess;
+    for (int k = 0; k < n_groups; ++k) {
+        const cudaError_t e = cudaStreamSynchronize(n_groups == 1 ? ctx->stream : ctx->group_stream[k]);
+        if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
+    }
+    if (first_err != cudaSuccess) return fail_cuda(ctx, first_err, "decode_parsed: stream synchronize");
+    int dev = 0;
+    CK(cudaMemcpy(&dev, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (dev != 0) { CK(cudaMemset(ctx->d_status, 0, sizeof(int))); return dev; }
+    return LLCOMP_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 int llcomp_b200_abi_version(void) { return LLCOMP_B200_ABI_VERSION; }
+void llcomp_b200_reload_switches(void) { reload_switches(); }
 
 const char* llcomp_b200_status_string(int s) {
     switch (s) {
@@ -250,6 +368,7 @@ int llcomp_b200_ctx_create(int device, llcomp_ctx** out) {
     }
     llcomp_ctx* ctx = new (std::nothrow) llcomp_ctx;
     if (!ctx) return LLCOMP_ERR_NOMEM;
+    reload_switches();
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -262,6 +381,7 @@ int llcomp_b200_ctx_create(int device, llcomp_ctx** out) {
         e = cudaMemGetInfo(&free_b, &total_b);
         ctx->queue_budget = (uint64_t)total_b * 2 / 5;       // 40 % of HBM (72 GB on B200)
     }
+    if (e == cudaSuccess) e = configure_frontend_rows();
     if (e == cudaSuccess) e = configure_slice_coder();
     if (e == cudaSuccess) e = configure_slice_decoder();
     if (e != cudaSuccess) {
@@ -318,6 +438,7 @@ int llcomp_b200_frontend_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const 
                                 void* cuda_stream) {
     Geom g;
     if (!ctx || !d_pixels || !d_sym || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     begin_call(ctx);
@@ -332,6 +453,7 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
                               uint64_t capacity, uint64_t* d_offsets, void* cuda_stream) {
     Geom g;
     if (!ctx || !d_pixels || !d_payload || !d_offsets || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const uint64_t ns = g.n_slices();
@@ -344,7 +466,7 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
     CK(ctx->h_qoff.reserve(ns));
     begin_call(ctx);
 
-    if (!getenv("LLCOMP_CODER_SPLIT")) {
+    if (!switches().coder_split) {
         // Default: front end, then ONE fused coder kernel (model + range chain + bytes per slice); fully asynchronous.
         const uint64_t gsb = fused_global_state_bytes(ns);
         if (gsb) CK(ctx->gstate.reserve(gsb));
@@ -411,6 +533,7 @@ int llcomp_b200_decode_device(llcomp_ctx* ctx, const uint8_t* d_payload, const u
                               const llcomp_geometry* gi, uint8_t* d_pixels, void* cuda_stream) {
     Geom g;
     if (!ctx || !d_payload || !d_offsets || !d_pixels || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const uint64_t lb = decoder_line_scratch_bytes(g);
@@ -427,6 +550,7 @@ int llcomp_b200_decode_device(llcomp_ctx* ctx, const uint8_t* d_payload, const u
 
 int llcomp_b200_finish(llcomp_ctx* ctx, void* cuda_stream) {
     if (!ctx) return LLCOMP_ERR_BAD_ARG;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
     int st = 0;
@@ -440,6 +564,7 @@ int llcomp_b200_encode_batch(llcomp_ctx* ctx, const uint8_t* pixels, const llcom
                              uint64_t out_cap, uint64_t* offsets) {
     Geom g;
     if (!ctx || !pixels || !out || !offsets || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     const uint64_t ns = g.n_slices(), cap = payload_capacity(g);
     const uint32_t spi = g.slices_per_image();
@@ -451,7 +576,7 @@ int llcomp_b200_encode_batch(llcomp_ctx* ctx, const uint8_t* pixels, const llcom
     // the coding of group k, and -- the coder being latency-bound per slice -- the groups' kernels overlap each
     // other on the GPU.  The state rows then have to live behind L1 (a shared-memory slot per slice would
     // serialise the groups).  The split coder (LLCOMP_CODER_SPLIT) and small batches take the single-call path.
-    const int n_groups = (getenv("LLCOMP_CODER_SPLIT") || g.n_images < 2 * llcomp_ctx::kGroups) ? 1 : llcomp_ctx::kGroups;
+    const int n_groups = (switches().coder_split || g.n_images < 2 * llcomp_ctx::kGroups) ? 1 : llcomp_ctx::kGroups;
     if (n_groups == 1) {
         CK(ctx->offsets.reserve(ns + 1));
         cudaStream_t st = ctx->stream;
@@ -563,52 +688,16 @@ int llcomp_b200_peek(const uint8_t* stream, size_t n, int* w, int* h, int* c, in
 int llcomp_b200_decode_batch(llcomp_ctx* ctx, const uint8_t* streams, const uint64_t* offsets, int n_images,
                              uint8_t* pixels_out, uint64_t pixels_cap, llcomp_geometry* g_out) {
     if (!ctx || !streams || !offsets || n_images < 1 || !pixels_out) return LLCOMP_ERR_BAD_ARG;
-    CK(cudaSetDevice(ctx->device));
-    llcomp_geometry gi{};
-    std::vector<uint64_t> off;          // slice offsets inside the contiguous device payload
-    std::vector<uint32_t> lens;
-    struct Piece { uint64_t src, dst, n; };
-    std::vector<Piece> pieces;          // host byte ranges that exist (the rest reads as zero, llcomp.hpp:476-477)
-    uint64_t total = 0;
-    off.push_back(0);
-    for (int k = 0; k < n_images; ++k) {
-        const uint8_t* s = streams + offsets[k];
-        const size_t n = (size_t)(offsets[k + 1] - offsets[k]);
-        llcomp_geometry gk; size_t hdr;
-        const int rc = parse_header(s, n, &gk, &hdr, &lens);
-        if (rc) return rc;
-        if (k == 0) gi = gk;
-        else if (gk.width != gi.width || gk.height != gi.height || gk.channels != gi.channels ||
-                 gk.tile_w != gi.tile_w || gk.tile_h != gi.tile_h) return LLCOMP_ERR_BAD_ARG;
-        uint64_t want = 0;
-        for (uint32_t L : lens) { want += L; off.push_back(total + want); }
-        const uint64_t have = std::min<uint64_t>(want, n - hdr);
-        if (have) pieces.push_back({offsets[k] + hdr, total, have});
-        total += want;
-    }
-    gi.n_images = n_images;
-    if (gi.width == 0 || gi.height == 0 || gi.channels == 0) {   // empty image: nothing to decode
-        if (g_out) *g_out = gi;
-        return LLCOMP_OK;
-    }
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    ParsedBatch pb;
+    int rc = parse_batch(streams, offsets, n_images, pb);
+    if (rc) return rc;
+    if (g_out) *g_out = pb.gi;
+    if (pb.gi.width == 0 || pb.gi.height == 0 || pb.gi.channels == 0) return LLCOMP_OK;   // empty image: nothing to decode
     Geom g;
-    if (!make_geom(&gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    if (!make_geom(&pb.gi, &g)) return LLCOMP_ERR_BAD_ARG;
     if (g.n_samples() > pixels_cap) return LLCOMP_ERR_OVERFLOW;
-    cudaStream_t st = ctx->stream;
-    CK(ctx->payload.reserve(total + 16));
-    CK(ctx->offsets.reserve(off.size()));
-    CK(ctx->pixels.reserve(g.n_samples()));
-    CK(cudaMemsetAsync(ctx->payload.p, 0, total + 16, st));
-    for (const Piece& p : pieces)
-        CK(cudaMemcpyAsync(ctx->payload.p + p.dst, streams + p.src, p.n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->offsets.p, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    int rc = llcomp_b200_decode_device(ctx, ctx->payload.p, ctx->offsets.p, &gi, ctx->pixels.p, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(pixels_out, ctx->pixels.p, g.n_samples(), cudaMemcpyDeviceToHost, st));
-    rc = llcomp_b200_finish(ctx, st);
-    if (rc) return rc;
-    if (g_out) *g_out = gi;
-    return LLCOMP_OK;
+    return decode_parsed(ctx, streams, pb, g, 0, g.n_images, pixels_out);
 }
 
 int llcomp_b200_decode(llcomp_ctx* ctx, const uint8_t* stream, size_t n, uint8_t** pixels, int* w, int* h, int* c) {
@@ -633,6 +722,264 @@ void llcomp_b200_free(void* p) { free(p); }
 uint32_t llcomp_b200_debug_table(int s) {
     static const ModelTables t = make_tables();
     return (s >= 0 && s < 128) ? t.entry[s] : 0;
+}
+
+}  // extern "C"
+
+// ---- several devices of one box ---------------------------------------------------------------------
+// Slices are independent (own payload, own state rows, own line buffers), so a batch or a large image is dealt to
+// the devices in contiguous blocks with no data-path exchange between them: one host thread and one
+// context per device; the only thing that crosses devices is the slice byte counts, on the host, to place every
+// device's payload in the one output.  The bytes are the single-device call's bytes.
+struct llcomp_multi {
+    std::vector<llcomp_ctx*> ctx;
+    std::mutex mu;                          // one call at a time
+};
+
+namespace {
+
+struct ShardPlan {
+    llcomp_ctx* ctx = nullptr;
+    llcomp_geometry gi{};
+    const uint8_t* px = nullptr;
+    int first_image = 0;
+    const uint64_t* off = nullptr;          // phase 1 result: slice offsets (pinned, owned by ctx)
+    int rc = LLCOMP_OK;
+    struct Copy { uint64_t p0, n; uint8_t* dst; };
+    std::vector<Copy> copies;               // phase 2: payload ranges -> their place in the caller's buffer
+};
+
+// Phase 1 on one device: pixels up, encode, slice offsets back.  The payload stays in ctx->payload.
+int shard_encode(ShardPlan& sh) {
+    llcomp_ctx* ctx = sh.ctx;
+    Geom g;
+    if (!make_geom(&sh.gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t ns = g.n_slices(), cap = payload_capacity(g);
+    CK(ctx->pixels.reserve(g.n_samples()));
+    CK(ctx->payload.reserve(cap));
+    CK(ctx->offsets.reserve(ns + 1));
+    CK(ctx->h_qoff.reserve(ns + 1));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->pixels.p, sh.px, g.n_samples(), cudaMemcpyHostToDevice, st));
+    int rc = llcomp_b200_encode_device(ctx, ctx->pixels.p, &sh.gi, ctx->payload.p, cap, ctx->offsets.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_qoff.p, ctx->offsets.p, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    rc = llcomp_b200_finish(ctx, st);
+    if (rc) return rc;
+    sh.off = ctx->h_qoff.p;
+    return LLCOMP_OK;
+}
+
+int shard_fetch(ShardPlan& sh) {
+    llcomp_ctx* ctx = sh.ctx;
+    CK(cudaSetDevice(ctx->device));
+    for (const ShardPlan::Copy& c : sh.copies)
+        if (c.n) CK(cudaMemcpyAsync(c.dst, ctx->payload.p + c.p0, c.n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LLCOMP_OK;
+}
+
+// Contiguous block [lo, hi) of part k out of n parts; blocks differ by at most one item.
+void block_of(int items, int k, int n, int* lo, int* hi) {
+    const int base = items / n, extra = items % n;
+    *lo = k * base + std::min(k, extra);
+    *hi = *lo + base + (k < extra ? 1 : 0);
+}
+
+// Runs fn(k) for k in [0, n) on n host threads, twice, with `between` on the calling thread in between (all first
+// halves have finished when it runs; it returns false to skip the second halves).  last(k) ends every thread.
+template <class F1, class Mid, class F2, class F3>
+void two_phase(int n, F1 first, Mid between, F2 second, F3 last) {
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0, go = 0;                // go: 0 wait, 1 run the second half, 2 skip it
+    std::vector<std::thread> th;
+    for (int k = 0; k < n; ++k)
+        th.emplace_back([&, k] {
+            first(k);
+            std::unique_lock<std::mutex> lk(m);
+            if (++arrived == n) cv.notify_all();
+            cv.wait(lk, [&] { return go != 0; });
+            const bool run = go == 1;
+            lk.unlock();
+            if (run) second(k);
+            last(k);                                         // on the worker thread either way
+        });
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return arrived == n; });
+    }
+    const bool ok = between();
+    {
+        std::lock_guard<std::mutex> lk(m);
+        go = ok ? 1 : 2;
+    }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int llcomp_b200_multi_create(const int* devices, int n_devices, llcomp_multi** out) {
+    if (!out) return LLCOMP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!devices || n_devices < 1) return LLCOMP_ERR_BAD_ARG;
+    llcomp_multi* m = new (std::nothrow) llcomp_multi;
+    if (!m) return LLCOMP_ERR_NOMEM;
+    for (int k = 0; k < n_devices; ++k) {
+        llcomp_ctx* c = nullptr;
+        const int rc = llcomp_b200_ctx_create(devices[k], &c);   // the same device may appear more than once
+        if (rc) { llcomp_b200_multi_destroy(m); return rc; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return LLCOMP_OK;
+}
+
+void llcomp_b200_multi_destroy(llcomp_multi* m) {
+    if (!m) return;
+    for (llcomp_ctx* c : m->ctx) llcomp_b200_ctx_destroy(c);
+    delete m;
+}
+
+int llcomp_b200_multi_device_count(const llcomp_multi* m) { return m ? (int)m->ctx.size() : 0; }
+llcomp_ctx* llcomp_b200_multi_ctx(llcomp_multi* m, int k) { return (m && k >= 0 && k < (int)m->ctx.size()) ? m->ctx[k] : nullptr; }
+
+int llcomp_b200_multi_encode_batch(llcomp_multi* m, const uint8_t* pixels, const llcomp_geometry* gi, uint8_t* out,
+                                   uint64_t out_cap, uint64_t* offsets) {
+    Geom g;
+    if (!m || !pixels || !out || !offsets || !make_geom(gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> call_lock(m->mu);
+    const int G = (int)m->ctx.size();
+    const uint32_t spi = g.slices_per_image();
+    const size_t hb = header_bytes(g);
+    const uint64_t img_bytes = g.image_samples();
+    // a batch goes image-wise; one image goes by bands of tile rows (each band is an image of its own to its device:
+    // tiles do not look outside themselves)
+    const bool bands = g.n_images == 1 && g.tiles_y >= 2 && G >= 2;
+    const int n_sh = bands ? std::min(G, g.tiles_y) : std::min(G, g.n_images);
+    std::vector<ShardPlan> sh(n_sh);
+    for (int k = 0; k < n_sh; ++k) {
+        int lo, hi;
+        block_of(bands ? g.tiles_y : g.n_images, k, n_sh, &lo, &hi);
+        sh[k].ctx = m->ctx[k];
+        sh[k].gi = *gi;
+        sh[k].gi.tile_w = g.tw;
+        sh[k].gi.tile_h = g.th;
+        if (bands) {
+            const int y0 = lo * g.th, y1 = std::min(g.H, hi * g.th);
+            sh[k].gi.height = y1 - y0;
+            sh[k].px = pixels + (uint64_t)y0 * g.W * g.C;
+        } else {
+            sh[k].gi.n_images = hi - lo;
+            sh[k].first_image = lo;
+            sh[k].px = pixels + (uint64_t)lo * img_bytes;
+        }
+    }
+    int status = LLCOMP_OK;
+    two_phase(
+        n_sh,
+        [&](int k) {
+            sh[k].ctx->mu.lock();                            // held across both halves: the payload stays in the context
+            sh[k].rc = shard_encode(sh[k]);
+        },
+        [&]() -> bool {
+            for (int k = 0; k < n_sh; ++k)
+                if (sh[k].rc) { status = sh[k].rc; return false; }
+            uint64_t pos = 0;
+            if (bands) {
+                std::vector<uint64_t> all(1, 0);             // slice offsets of the whole image
+                for (int k = 0; k < n_sh; ++k) {
+                    Geom gk;
+                    make_geom(&sh[k].gi, &gk);
+                    const uint64_t nk = gk.n_slices();
+                    for (uint64_t i = 1; i <= nk; ++i) all.push_back(all.back() + (sh[k].off[i] - sh[k].off[i - 1]));
+                }
+                if (all.size() != (size_t)spi + 1) { status = LLCOMP_ERR_BAD_ARG; return false; }
+                if (hb + all.back() > out_cap) { status = LLCOMP_ERR_OVERFLOW; return false; }
+                write_header(g, all.data(), out);
+                pos = hb;
+                for (int k = 0; k < n_sh; ++k) {
+                    Geom gk;
+                    make_geom(&sh[k].gi, &gk);
+                    const uint64_t nb = sh[k].off[gk.n_slices()];
+                    sh[k].copies.push_back({0, nb, out + pos});
+                    pos += nb;
+                }
+                offsets[0] = 0;
+                offsets[1] = pos;
+                return true;
+            }
+            for (int k = 0; k < n_sh; ++k)
+                for (int i = 0; i < sh[k].gi.n_images; ++i) {
+                    const uint64_t* o = sh[k].off + (uint64_t)i * spi;
+                    const uint64_t p0 = o[0], p1 = o[spi];
+                    offsets[sh[k].first_image + i] = pos;
+                    if (pos + hb + (p1 - p0) > out_cap) { status = LLCOMP_ERR_OVERFLOW; return false; }
+                    write_header(g, o, out + pos);
+                    sh[k].copies.push_back({p0, p1 - p0, out + pos + hb});
+                    pos += hb + (p1 - p0);
+                }
+            offsets[g.n_images] = pos;
+            return true;
+        },
+        [&](int k) { sh[k].rc = shard_fetch(sh[k]); },
+        [&](int k) { sh[k].ctx->mu.unlock(); });
+    for (int k = 0; k < n_sh; ++k)
+        if (status == LLCOMP_OK && sh[k].rc) status = sh[k].rc;
+    return status;
+}
+
+int llcomp_b200_multi_decode_batch(llcomp_multi* m, const uint8_t* streams, const uint64_t* offsets, int n_images,
+                                   uint8_t* pixels_out, uint64_t pixels_cap, llcomp_geometry* g_out) {
+    if (!m || !streams || !offsets || n_images < 1 || !pixels_out) return LLCOMP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> call_lock(m->mu);
+    ParsedBatch pb;
+    int rc = parse_batch(streams, offsets, n_images, pb);
+    if (rc) return rc;
+    if (g_out) *g_out = pb.gi;
+    if (pb.gi.width == 0 || pb.gi.height == 0 || pb.gi.channels == 0) return LLCOMP_OK;
+    Geom g;
+    if (!make_geom(&pb.gi, &g)) return LLCOMP_ERR_BAD_ARG;
+    if (g.n_samples() > pixels_cap) return LLCOMP_ERR_OVERFLOW;
+    const int G = (int)m->ctx.size();
+    const bool bands = n_images == 1 && g.tiles_y >= 2 && G >= 2;
+    const int n_sh = bands ? std::min(G, g.tiles_y) : std::min(G, n_images);
+    std::vector<int> rcs(n_sh, LLCOMP_OK);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n_sh; ++k)
+        th.emplace_back([&, k] {
+            int lo, hi;
+            block_of(bands ? g.tiles_y : n_images, k, n_sh, &lo, &hi);
+            llcomp_ctx* ctx = m->ctx[k];
+            std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+            if (!bands) {
+                rcs[k] = decode_parsed(ctx, streams, pb, g, lo, hi - lo, pixels_out + (uint64_t)lo * g.image_samples());
+                return;
+            }
+            // the band as a one-image batch of its own: tile rows [lo, hi) of the image
+            const int y0 = lo * g.th, y1 = std::min(g.H, hi * g.th);
+            const uint64_t sl0 = (uint64_t)lo * g.tiles_x, sl1 = (uint64_t)hi * g.tiles_x;
+            ParsedBatch band;
+            band.gi = pb.gi;
+            band.gi.height = y1 - y0;
+            band.gi.n_images = 1;
+            const uint64_t b0 = pb.off[sl0], b1 = pb.off[sl1];
+            for (uint64_t s = sl0; s <= sl1; ++s) band.off.push_back(pb.off[s] - b0);
+            const ParsedBatch::Piece& whole = pb.pieces[0];
+            const uint64_t have = whole.have > b0 ? std::min(whole.have, b1) - b0 : 0;
+            band.pieces.push_back({whole.src + b0, 0, have, b1 - b0});
+            Geom gb;
+            if (!make_geom(&band.gi, &gb)) { rcs[k] = LLCOMP_ERR_BAD_ARG; return; }
+            rcs[k] = decode_parsed(ctx, streams, band, gb, 0, 1, pixels_out + (uint64_t)y0 * g.W * g.C);
+        });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < n_sh; ++k)
+        if (rcs[k]) return rcs[k];
+    return LLCOMP_OK;
 }
 
 }  // extern "C"

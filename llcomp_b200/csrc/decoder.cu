@@ -403,12 +403,15 @@ static bool fast_decoder_fits(const Geom& g) {
 }
 // State in shared memory while every slice of the call finds a shared-memory slot at once (3 per SM for
 // <= 1024-wide RGB tiles), else state in global memory behind L1 (7+ slices per SM, one wave).
-static bool decoder_wants_global_state(const Geom& g) {
+static bool decoder_wants_global_state(const Geom& g, bool shared_launch) {
     const int per_sm = (228 * 1024) / (kFastBase + fast_line_bytes(g) + 1024);
-    return fast_decoder_fits(g) && g.n_slices() > (uint64_t)per_sm * 148 && !getenv("LLCOMP_DECODER_SMEM_STATE");
+    if (!fast_decoder_fits(g) || switches().decoder_smem_state) return false;
+    // a launch that runs beside other launches of the same call (pipelined host-buffer decode) must not take
+    // shared-memory slots away from them
+    return shared_launch || g.n_slices() > (uint64_t)per_sm * 148;
 }
-uint64_t decoder_global_state_bytes(const Geom& g) {
-    return decoder_wants_global_state(g) ? g.n_slices() * (uint64_t)kStateBytes : 0;
+uint64_t decoder_global_state_bytes(const Geom& g, bool shared_launch) {
+    return decoder_wants_global_state(g, shared_launch) ? g.n_slices() * (uint64_t)kStateBytes : 0;
 }
 
 static bool lines_fit_smem(const Geom& g) {
@@ -436,12 +439,12 @@ cudaError_t configure_slice_decoder() {
 
 cudaError_t launch_slice_decoder(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
                                  uint8_t* d_pixels, int16_t* d_line_scratch, uint8_t* d_gstate, int* d_status,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, bool shared_launch) {
     const uint64_t ns = g.n_slices();
     if (ns == 0 || ns > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    if (fast_decoder_fits(g) && !getenv("LLCOMP_DECODER_SIMPLE")) {
+    if (fast_decoder_fits(g) && !switches().decoder_simple) {
         const unsigned n = (unsigned)ns;
-        if (decoder_wants_global_state(g)) {
+        if (decoder_wants_global_state(g, shared_launch)) {
             const int smem = kFastBase - kStateBytes + fast_line_bytes(g);
             uint2* gs = reinterpret_cast<uint2*>(d_gstate);
             cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);   // all states start at 0

@@ -267,7 +267,11 @@ __global__ void __launch_bounds__(256, 5) k_frontend_tiled(const uint8_t* __rest
 cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, unsigned long long* d_slice_bins,
                             cudaStream_t st) {
     if (g.H > 65535 * kTileH || g.n_images > 65535) return cudaErrorInvalidValue;
-    if ((g.C == 3 || g.C == 4) && g.th >= kTileH && !getenv("LLCOMP_FRONTEND_SIMPLE")) {
+    const Switches& sw = switches();
+    const bool no_rows = sw.frontend_tiled || sw.frontend_simple;
+    if (!d_slice_bins && !no_rows && frontend_rows_applicable(d_pixels, g)) return launch_frontend_rows(d_pixels, g, d_sym, st);
+    // the tiled kernel indexes records inside an image with 32 bits
+    if (g.image_samples() < (1ull << 32) && (g.C == 3 || g.C == 4) && g.th >= kTileH && !sw.frontend_simple) {
         dim3 grid((g.W + kTileW - 1) / kTileW, (g.H + kTileH - 1) / kTileH, g.n_images);
         if (g.C == 3 && d_slice_bins) k_frontend_tiled<3, true><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, d_slice_bins);
         else if (g.C == 3) k_frontend_tiled<3, false><<<grid, 256, 0, st>>>(d_pixels, g, d_sym, nullptr);

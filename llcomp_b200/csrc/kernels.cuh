@@ -4,10 +4,30 @@
 
 namespace llc {
 
+// Test switches (DESIGN.md "Test switches"): each selects the plain variant of one stage so that tests can check the
+// default kernels against it; none selects a CPU path.  Read from the environment (LLCOMP_*) when a context is
+// created and again by llcomp_b200_reload_switches(); the launchers never call getenv themselves.
+struct Switches {
+    bool frontend_simple = false;     // LLCOMP_FRONTEND_SIMPLE   one thread per pixel
+    bool frontend_tiled = false;      // LLCOMP_FRONTEND_TILED    round-1 tiled front end instead of the streaming one
+    bool decoder_simple = false;      // LLCOMP_DECODER_SIMPLE    plain chain, three row buffers
+    bool coder_split = false;         // LLCOMP_CODER_SPLIT       model pass -> HBM queue -> range pass
+    bool decoder_smem_state = false;  // LLCOMP_DECODER_SMEM_STATE
+    bool model_smem_state = false;    // LLCOMP_MODEL_SMEM_STATE
+    int fused_ns = 0;                 // LLCOMP_FUSED_NS          slices per coder CTA; 0 = automatic
+};
+const Switches& switches();
+void reload_switches();
+
 // K1  pixels -> records, plus the exact number of binary decisions of every slice (frontend.cu).
 //     d_slice_bins (n_slices counters) must be zero on entry; nullptr skips the counting.
 cudaError_t launch_frontend(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym,
                             unsigned long long* d_slice_bins, cudaStream_t st);
+
+// K1, streaming form (frontend_rows.cu): TMA row loads, rows carried in registers, 128-bit stores.
+bool frontend_rows_applicable(const uint8_t* d_pixels, const Geom& g);
+cudaError_t launch_frontend_rows(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st);
+cudaError_t configure_frontend_rows();
 
 // K2a records -> bin queue (model pass, state in shared memory); K2b bin queue -> per-slice scratch payloads
 //     and byte counts (range pass).  Both work on slices [s0, s0+count); d_qoff[s] = first queue entry of slice s.
@@ -33,11 +53,13 @@ cudaError_t launch_compact(const uint8_t* d_scratch, const Geom& g, const uint64
                            uint8_t* d_payload, uint64_t capacity, cudaStream_t st);
 
 // K5  payloads -> pixels (decoder.cu)
+//     shared_launch: the launch runs beside other decoder launches of the same call (pipelined host-buffer decode);
+//     its state rows then always live in d_gstate.
 cudaError_t launch_slice_decoder(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
                                  uint8_t* d_pixels, int16_t* d_line_scratch, uint8_t* d_gstate, int* d_status,
-                                 cudaStream_t st);
+                                 cudaStream_t st, bool shared_launch = false);
 // bytes of global state the decoder wants for this geometry (0 when the state stays in shared memory)
-uint64_t decoder_global_state_bytes(const Geom& g);
+uint64_t decoder_global_state_bytes(const Geom& g, bool shared_launch = false);
 cudaError_t configure_slice_decoder();
 // bytes of global line scratch the decoder needs for this geometry (0 when the rows fit in shared memory)
 uint64_t decoder_line_scratch_bytes(const Geom& g);

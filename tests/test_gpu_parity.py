@@ -23,6 +23,23 @@ def codec():
     return llcomp_b200.default_codec(0)
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def switched(codec, **env):
+    """Run a block with LLCOMP_* test switches set (the library samples them at context creation, so tell it)."""
+    for k, v in env.items():
+        os.environ[k] = str(v)
+    codec.reload_switches()
+    try:
+        yield
+    finally:
+        for k in env:
+            del os.environ[k]
+        codec.reload_switches()
+
+
 def split_container(stream: bytes):
     """(w, h, c, tile_w, tile_h, [payload per slice]) of either stream layout."""
     if stream[0] == 0x79:
@@ -88,7 +105,11 @@ def test_module_level_functions_mirror_reference_api():
 @pytest.mark.parametrize("w,h,c,tw,th,amp", [
     (64, 48, 3, 0, 0, 8), (65, 33, 3, 16, 16, 4), (37, 29, 1, 0, 0, 16), (37, 29, 2, 8, 32, 2),
     (50, 40, 4, 32, 8, 128), (19, 23, 5, 7, 5, 6), (1, 1, 3, 0, 0, 0), (1, 9, 3, 0, 0, 9), (9, 1, 3, 4, 1, 9),
-    (2, 2, 3, 1, 1, 50), (300, 70, 3, 128, 64, 5)])
+    (2, 2, 3, 1, 1, 50), (300, 70, 3, 128, 64, 5),
+    # the streaming kernel (W*C % 16 == 0, tile_w % 4 == 0): whole rows, partial last region, tile rows that end
+    # inside a region, one-group tiles (left and right edge in the same thread), rows that are all h < 2
+    (1024, 70, 3, 0, 0, 4), (1040, 67, 3, 512, 32, 6), (528, 40, 4, 132, 9, 5), (16, 5, 3, 4, 2, 30),
+    (32, 40, 3, 8, 3, 10), (2048, 35, 3, 1024, 33, 64), (64, 100, 4, 64, 100, 128)])
 def test_frontend_records_equal_oracle(codec, w, h, c, tw, th, amp):
     import torch
     rng = np.random.default_rng(w * 1000 + h)
@@ -251,15 +272,14 @@ def test_split_coder_path_and_launch_groups(codec):
     d_px = torch.from_numpy(imgs).cuda()
     ref_payload, ref_off = codec.encode_device(d_px, g)          # default: fused coder
     codec.finish()
-    os.environ["LLCOMP_CODER_SPLIT"] = "1"
     codec.set_queue_budget(200_000)                 # ~3 slices per group instead of all 28
     try:
-        payload, off = codec.encode_device(d_px, g)
-        codec.finish()
-        assert codec.last_bin_count() == sum(oracle.count_bins(imgs[k][y0:y0 + 48, x0:x0 + 64]) for k in range(7)
-                                             for (x0, y0, _, _) in tiles_of(128, 96, 64, 48))
+        with switched(codec, LLCOMP_CODER_SPLIT=1):
+            payload, off = codec.encode_device(d_px, g)
+            codec.finish()
+            assert codec.last_bin_count() == sum(oracle.count_bins(imgs[k][y0:y0 + 48, x0:x0 + 64]) for k in range(7)
+                                                 for (x0, y0, _, _) in tiles_of(128, 96, 64, 48))
     finally:
-        del os.environ["LLCOMP_CODER_SPLIT"]
         codec.set_queue_budget(64 << 30)
     assert torch.equal(off, ref_off)
     n = int(off[-1])
@@ -279,16 +299,12 @@ def test_many_slices_decode_with_state_behind_l1(codec):
     out = codec.decode_device(payload, offsets, g)
     codec.finish()
     assert torch.equal(out.view(16, 192, 256, 3), d_px)
-    os.environ["LLCOMP_DECODER_SMEM_STATE"] = "1"                     # same answer with the state in shared memory
-    os.environ["LLCOMP_CODER_SPLIT"] = "1"                            # ... and from the two-kernel coder
-    try:
+    # same answer with the state in shared memory, and from the two-kernel coder
+    with switched(codec, LLCOMP_DECODER_SMEM_STATE=1, LLCOMP_CODER_SPLIT=1):
         out2 = codec.decode_device(payload, offsets, g)
         codec.finish()
         payload2, offsets2 = codec.encode_device(d_px, g)
         codec.finish()
-    finally:
-        del os.environ["LLCOMP_DECODER_SMEM_STATE"]
-        del os.environ["LLCOMP_CODER_SPLIT"]
     assert torch.equal(out2, out)
     assert torch.equal(offsets2, offsets) and torch.equal(payload2[: int(offsets[-1])], payload[: int(offsets[-1])])
     off = offsets.cpu().numpy()
@@ -298,9 +314,10 @@ def test_many_slices_decode_with_state_behind_l1(codec):
 
 
 def test_fused_coder_variants_agree(codec):
-    """The fused coder serves 1, 2 or 4 slices per chain warp (LLCOMP_FUSED_NS) with the state rows behind L1, or one
-    slice per CTA with the rows in shared memory (LLCOMP_MODEL_SMEM_STATE): same bytes from all of them, with ragged
-    slices and a slice count (378) that leaves the last CTA of the 4-slice form half empty."""
+    """The fused coder serves 3..7 slices per CTA with one CTA per SM (the default picks by slice count; 13..17 force
+    it), or 1, 2, 4 slices per chain warp in the round-1 arrangement (LLCOMP_FUSED_NS), always with the state rows
+    behind L1, or one slice per CTA with the rows in shared memory (LLCOMP_MODEL_SMEM_STATE): same bytes from all of
+    them, with ragged slices and a slice count (378) that leaves the last CTA of every form partly empty."""
     import torch
     imgs = np.stack([oracle.generate(200, 180, 3, 9, 4100 + k) for k in range(9)])
     g = codec.geometry(200, 180, 3, 32, 32, 9)                       # 7 x 6 tiles (last column 8 wide, last row 20 high)
@@ -310,13 +327,11 @@ def test_fused_coder_variants_agree(codec):
     codec.finish()
     n = int(offsets[-1])
     for var, val in (("LLCOMP_FUSED_NS", "1"), ("LLCOMP_FUSED_NS", "2"), ("LLCOMP_FUSED_NS", "4"),
-                     ("LLCOMP_MODEL_SMEM_STATE", "1")):
-        os.environ[var] = val
-        try:
+                     ("LLCOMP_FUSED_NS", "14"), ("LLCOMP_FUSED_NS", "15"), ("LLCOMP_FUSED_NS", "16"),
+                     ("LLCOMP_FUSED_NS", "17"), ("LLCOMP_MODEL_SMEM_STATE", "1")):
+        with switched(codec, **{var: val}):
             p2, o2 = codec.encode_device(d_px, g)
             codec.finish()
-        finally:
-            del os.environ[var]
         assert torch.equal(o2, offsets) and torch.equal(p2[:n], payload[:n]), (var, val)
     off = offsets.cpu().numpy()
     tiles = tiles_of(200, 180, 32, 32)
@@ -355,22 +370,19 @@ def test_alternate_kernels_agree(codec):
     """Every stage has a plain variant behind a switch (one-thread-per-pixel front end, plain decoder chain,
     two-kernel coder); all of them must produce the same bytes / pixels as the default kernels."""
     import torch
-    imgs = np.stack([oracle.generate(200, 144, 3, 5, 900 + k) for k in range(3)])
-    g = codec.geometry(200, 144, 3, 96, 64, 3)
+    imgs = np.stack([oracle.generate(208, 144, 3, 5, 900 + k) for k in range(3)])    # 208*3 % 16 == 0: streaming K1
+    g = codec.geometry(208, 144, 3, 96, 64, 3)
     d_px = torch.from_numpy(imgs).cuda()
     payload, offsets = codec.encode_device(d_px, g)
     out = codec.decode_device(payload, offsets, g)
     codec.finish()
     n = int(offsets[-1])
     assert torch.equal(out.view(imgs.shape), d_px)
-    for switch in ("LLCOMP_FRONTEND_SIMPLE", "LLCOMP_DECODER_SIMPLE", "LLCOMP_CODER_SPLIT"):
-        os.environ[switch] = "1"
-        try:
+    for switch in ("LLCOMP_FRONTEND_SIMPLE", "LLCOMP_FRONTEND_TILED", "LLCOMP_DECODER_SIMPLE", "LLCOMP_CODER_SPLIT"):
+        with switched(codec, **{switch: 1}):
             p2, o2 = codec.encode_device(d_px, g)
             out2 = codec.decode_device(p2, o2, g)
             codec.finish()
-        finally:
-            del os.environ[switch]
         assert torch.equal(o2, offsets) and torch.equal(p2[:n], payload[:n]), switch
         assert torch.equal(out2, out), switch
 
