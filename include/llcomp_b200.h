@@ -141,6 +141,11 @@ uint64_t llcomp_b200_last_bin_count(const llcomp_ctx *ctx);
 /* Only for the two-kernel coder kept behind LLCOMP_CODER_SPLIT=1 (the default fused coder has no queue):
  * bytes of HBM its bin queue may take; default 40 % of the device.  Tests shrink it to force launch groups. */
 void llcomp_b200_set_queue_budget(llcomp_ctx *ctx, uint64_t bytes);
+/* The front end's records (4 bytes per sample) go through an array in HBM while it fits `bytes` (default: a third of the
+ * device) and the free memory; beyond that the coder computes them from the pixels inside its CTAs (3- and 4-channel
+ * images; a few percent slower, no array).  0 = always from the pixels.  The second call says what the last encode did. */
+void llcomp_b200_set_record_budget(llcomp_ctx *ctx, uint64_t bytes);
+int llcomp_b200_last_encode_from_pixels(const llcomp_ctx *ctx);
 /* Test switches (LLCOMP_FRONTEND_SIMPLE, LLCOMP_FRONTEND_TILED, LLCOMP_DECODER_SIMPLE, LLCOMP_CODER_SPLIT,
  * LLCOMP_DECODER_SMEM_STATE, LLCOMP_MODEL_SMEM_STATE, LLCOMP_FUSED_NS) select the plain GPU variant of a stage.  They are
  * read from the environment when a context is created; call this after changing them in a live process. */

@@ -54,6 +54,8 @@ SIGNATURES = {
     "llcomp_b200_debug_table": (C.c_uint32, [C.c_int]),
     "llcomp_b200_set_queue_budget": (None, [_vp, C.c_uint64]),
     "llcomp_b200_last_bin_count": (C.c_uint64, [_vp]),
+    "llcomp_b200_set_record_budget": (None, [_vp, C.c_uint64]),
+    "llcomp_b200_last_encode_from_pixels": (C.c_int, [_vp]),
     "llcomp_b200_reload_switches": (None, []),
     "llcomp_b200_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
     "llcomp_b200_multi_destroy": (None, [_vp]),

@@ -224,6 +224,14 @@ class Codec:
         """HBM the encoder's bin queue may take (default 40 % of the device); smaller forces more launch groups."""
         self._L.llcomp_b200_set_queue_budget(self._h, int(nbytes))
 
+    def set_record_budget(self, nbytes: int):
+        """HBM the front end's record array may take (default a third of the device); beyond it -- or with 0 -- the
+        coder computes its records from the pixels and no array exists."""
+        self._L.llcomp_b200_set_record_budget(self._h, int(nbytes))
+
+    def last_encode_from_pixels(self) -> bool:
+        return bool(self._L.llcomp_b200_last_encode_from_pixels(self._h))
+
     def stage_times(self) -> dict:
         ms = (C.c_float * _capi.N_STAGES)()
         self._check(self._L.llcomp_b200_stage_times(self._h, ms))

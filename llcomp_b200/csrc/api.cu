@@ -19,6 +19,8 @@
 
 using namespace llc;
 
+constexpr int llcomp_ctx_groups = 4;   // streams a host-buffer call may pipeline its image groups over
+
 namespace llc {
 static Switches g_switches;
 const Switches& switches() { return g_switches; }
@@ -31,7 +33,10 @@ void reload_switches() {
     s.coder_split = on("LLCOMP_CODER_SPLIT");
     s.decoder_smem_state = on("LLCOMP_DECODER_SMEM_STATE");
     s.model_smem_state = on("LLCOMP_MODEL_SMEM_STATE");
+    s.coder_records = on("LLCOMP_CODER_RECORDS");
+    s.coder_pixels = on("LLCOMP_CODER_PIXELS");
     if (const char* v = getenv("LLCOMP_FUSED_NS")) s.fused_ns = atoi(v);
+    if (const char* v = getenv("LLCOMP_GROUPS")) s.groups = std::max(0, std::min(atoi(v), (int)llcomp_ctx_groups));
     g_switches = s;
 }
 }  // namespace llc
@@ -78,7 +83,7 @@ struct llcomp_ctx {
     std::recursive_mutex mu;                // one call at a time per context (the work buffers below are shared)
     int device = 0;
     cudaStream_t stream = nullptr;          // used by the host-buffer entry points
-    static constexpr int kGroups = 4;       // host-buffer encode: image groups pipelined over this many streams
+    static constexpr int kGroups = llcomp_ctx_groups;   // host-buffer calls: image groups pipelined over this many streams
     cudaStream_t group_stream[kGroups] = {};
     DevBuf<uint32_t> sym;                   // K1 -> K2a records
     DevBuf<unsigned long long> slice_bins;  // K1: exact number of binary decisions per slice
@@ -86,8 +91,10 @@ struct llcomp_ctx {
     DevBuf<uint16_t> queue;                 // K2a -> K2b bin queue
     PinnedBuf<unsigned long long> h_bins;
     PinnedBuf<uint64_t> h_qoff;
+    bool from_pixels = false;               // the current fused encode computes its records from the pixels (no record array)
     uint64_t last_bins = 0;                 // decisions coded by the last encode call
     uint64_t queue_budget = 0;              // bytes the bin queue may take; slices are processed in groups that fit
+    uint64_t record_budget = 0;             // bytes K1's record array may take; beyond, the coder works from the pixels
     DevBuf<uint8_t> scratch;                // K2b per-slice payloads before compaction
     DevBuf<uint32_t> slice_bytes;
     DevBuf<int16_t> lines;                  // K5 row scratch when a tile row does not fit in smem
@@ -209,23 +216,49 @@ struct StageScope {
     ~StageScope() { if (b) cudaEventRecord(b, st); }
 };
 
+// The record array K1 writes for the coder (4 bytes per sample), unless the fused coder is to compute its records from
+// the pixels: forced by a switch, or because the array does not fit (it is then not worth a third of the device either).
+cudaError_t reserve_records(llcomp_ctx* ctx, const Geom& g) {
+    ctx->from_pixels = false;
+    const size_t need = g.n_samples();
+    if (switches().coder_split) return ctx->sym.reserve(need);
+    if (fused_coder_takes_pixels(g, true)) { ctx->from_pixels = true; return cudaSuccess; }   // forced by a switch
+    const bool may_fall_back = fused_coder_takes_pixels(g, false);
+    if (may_fall_back && need * 4 > ctx->record_budget) { ctx->sym.release(); ctx->from_pixels = true; return cudaSuccess; }
+    if (need <= ctx->sym.cap) return cudaSuccess;
+    if (may_fall_back) {
+        size_t free_b = 0, total_b = 0;
+        const bool roomy = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need * 4 + (1ull << 30) <= free_b + ctx->sym.cap * 4;
+        if (!roomy) { ctx->sym.release(); ctx->from_pixels = true; return cudaSuccess; }
+    }
+    const cudaError_t e = ctx->sym.reserve(need);
+    if (e == cudaErrorMemoryAllocation && may_fall_back) {
+        (void)cudaGetLastError();
+        ctx->from_pixels = true;
+        return cudaSuccess;
+    }
+    return e;
+}
+
 // Front end + fused coder + scan + compaction of the images [first_image, first_image + g.n_images) of a batch
 // whose workspace (records, scratch, byte counts, state rows) was reserved for the whole batch: every buffer is
 // linear in the image index, so a group of images simply works on its own stretch of each.
 int encode_fused_on(llcomp_ctx* ctx, const uint8_t* d_pixels, const Geom& g, uint64_t first_image, bool global_state,
-                    uint8_t* d_payload, uint64_t capacity, uint64_t* d_offsets, cudaStream_t st) {
+                    uint8_t* d_payload, uint64_t capacity, uint64_t* d_offsets, cudaStream_t st, uint64_t n_concurrent = 0) {
     const uint64_t spi = g.slices_per_image(), first_slice = first_image * spi;
-    uint32_t* sym = ctx->sym.p + first_image * g.image_samples();
+    const bool from_pixels = ctx->from_pixels;               // no record array then (the caller has not reserved one)
+    uint32_t* sym = from_pixels ? nullptr : ctx->sym.p + first_image * g.image_samples();
     uint8_t* scratch = ctx->scratch.p + first_image * (2 * g.image_samples() + kScratchSlack * spi);
     uint32_t* slice_bytes = ctx->slice_bytes.p + first_slice;
     uint8_t* gstate = global_state ? ctx->gstate.p + first_slice * (uint64_t)kStateBytes : nullptr;
-    {
+    if (!from_pixels) {
         StageScope sc(ctx, st, kStFrontend);
         CK(launch_frontend(d_pixels, g, sym, nullptr, st));
     }
     {
         StageScope sc(ctx, st, kStRange);
-        CK(launch_slice_coder_fused(sym, g, scratch, slice_bytes, ctx->d_status, gstate, st));
+        CK(launch_slice_coder_fused(sym, from_pixels ? d_pixels : nullptr, g, scratch, slice_bytes, ctx->d_status, gstate, st,
+                                    n_concurrent));
     }
     {
         StageScope sc(ctx, st, kStScan);
@@ -283,7 +316,9 @@ int decode_parsed(llcomp_ctx* ctx, const uint8_t* streams, const ParsedBatch& pb
     const uint64_t spi = g.slices_per_image(), ns = g.n_slices(), img_bytes = g.image_samples();
     const uint64_t s0 = (uint64_t)first * spi;
     const uint64_t pay0 = pb.off[s0], pay_bytes = pb.off[s0 + ns] - pay0;
-    const int n_groups = count >= 2 * llcomp_ctx::kGroups ? llcomp_ctx::kGroups : 1;
+    // (two groups: the copies are a twentieth of the decode time, and four launches side by side decode slower than two)
+    const int want_groups = switches().groups ? switches().groups : 2;
+    const int n_groups = count >= 2 * want_groups ? want_groups : 1;
     const bool shared = n_groups > 1;
     CK(ctx->payload.reserve(pay_bytes + 16));
     CK(ctx->offsets.reserve(ns + n_groups));
@@ -380,6 +415,7 @@ int llcomp_b200_ctx_create(int device, llcomp_ctx** out) {
         size_t free_b = 0, total_b = 0;
         e = cudaMemGetInfo(&free_b, &total_b);
         ctx->queue_budget = (uint64_t)total_b * 2 / 5;       // 40 % of HBM (72 GB on B200)
+        ctx->record_budget = (uint64_t)total_b / 3;          // a third of HBM (60 GB: 15 G samples per call)
     }
     if (e == cudaSuccess) e = configure_frontend_rows();
     if (e == cudaSuccess) e = configure_slice_coder();
@@ -432,6 +468,8 @@ int llcomp_b200_stage_times(llcomp_ctx* ctx, float* ms) {
 
 uint64_t llcomp_b200_last_bin_count(const llcomp_ctx* ctx) { return ctx ? ctx->last_bins : 0; }
 void llcomp_b200_set_queue_budget(llcomp_ctx* ctx, uint64_t bytes) { if (ctx && bytes) ctx->queue_budget = bytes; }
+void llcomp_b200_set_record_budget(llcomp_ctx* ctx, uint64_t bytes) { if (ctx) ctx->record_budget = bytes; }
+int llcomp_b200_last_encode_from_pixels(const llcomp_ctx* ctx) { return ctx && ctx->from_pixels; }
 
 // ---- device-resident path --------------------------------------------------------------------
 int llcomp_b200_frontend_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const llcomp_geometry* gi, uint32_t* d_sym,
@@ -457,7 +495,7 @@ int llcomp_b200_encode_device(llcomp_ctx* ctx, const uint8_t* d_pixels, const ll
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const uint64_t ns = g.n_slices();
-    CK(ctx->sym.reserve(g.n_samples()));
+    CK(reserve_records(ctx, g));
     CK(ctx->scratch.reserve(payload_capacity(g) + 64));
     CK(ctx->slice_bytes.reserve(ns));
     CK(ctx->slice_bins.reserve(ns));
@@ -576,7 +614,10 @@ int llcomp_b200_encode_batch(llcomp_ctx* ctx, const uint8_t* pixels, const llcom
     // the coding of group k, and -- the coder being latency-bound per slice -- the groups' kernels overlap each
     // other on the GPU.  The state rows then have to live behind L1 (a shared-memory slot per slice would
     // serialise the groups).  The split coder (LLCOMP_CODER_SPLIT) and small batches take the single-call path.
-    const int n_groups = (switches().coder_split || g.n_images < 2 * llcomp_ctx::kGroups) ? 1 : llcomp_ctx::kGroups;
+    // (the groups' coder launches run side by side: each is told how many slices are resident in all, so that together
+    // they fill the device once instead of each sizing its CTAs as if it were alone)
+    const int want_groups = switches().groups ? switches().groups : llcomp_ctx::kGroups;
+    const int n_groups = (switches().coder_split || g.n_images < 2 * want_groups) ? 1 : want_groups;
     if (n_groups == 1) {
         CK(ctx->offsets.reserve(ns + 1));
         cudaStream_t st = ctx->stream;
@@ -601,7 +642,7 @@ int llcomp_b200_encode_batch(llcomp_ctx* ctx, const uint8_t* pixels, const llcom
         return LLCOMP_OK;
     }
 
-    CK(ctx->sym.reserve(g.n_samples()));
+    CK(reserve_records(ctx, g));
     CK(ctx->scratch.reserve(cap + 64));
     CK(ctx->slice_bytes.reserve(ns));
     CK(ctx->gstate.reserve(ns * (uint64_t)kStateBytes));
@@ -628,7 +669,7 @@ int llcomp_b200_encode_batch(llcomp_ctx* ctx, const uint8_t* pixels, const llcom
         CK(cudaMemcpyAsync(d_px, pixels + (uint64_t)pt.first * img_bytes, (uint64_t)pt.count * img_bytes,
                            cudaMemcpyHostToDevice, st));
         const int rc = encode_fused_on(ctx, d_px, gg, pt.first, true, ctx->payload.p + (uint64_t)pt.first * img_cap,
-                                       (uint64_t)pt.count * img_cap, d_off, st);
+                                       (uint64_t)pt.count * img_cap, d_off, st, ns);
         if (rc) return rc;
         off[k] = ctx->h_qoff.p + pt.slice0 + k;
         CK(cudaMemcpyAsync(off[k], d_off, ((uint64_t)pt.count * spi + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));

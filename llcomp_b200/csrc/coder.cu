@@ -17,15 +17,18 @@
 //                         between them (LLCOMP_CODER_SPLIT=1; kept as a cross-check of the fused kernel).
 // The slice's 63,408 bytes of state rows live in shared memory while every slice of the launch finds a slot,
 // else in global memory behind L1.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sample.cuh"
 
 namespace llc {
 
 __constant__ ModelTables c_tables = make_tables();
+__constant__ QuantBytes c_quant_bytes_coder = make_quant_bytes();
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -55,9 +58,14 @@ constexpr int kModelSmem = kRowBytesSmem + 256 * 4;          // + tab2
 
 // Where the model pass puts its 16-bit entries: the bin queue in HBM (split kernels) or a shared-memory FIFO
 // (fused kernel).  `pos` counts from the first decision of the current 32-sample step.
+// A sink turns the position of a sample's first decision into an address once (at) and then takes the sample's
+// entries at small offsets from it (put): the offsets are compile-time constants or running sums, so an entry costs
+// one store and no address arithmetic.
 struct QueueSink {
     uint16_t* q;
-    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const { q[pos] = (uint16_t)w; }
+    typedef uint16_t* Addr;
+    __device__ __forceinline__ Addr at(uint32_t pos) const { return q + pos; }
+    __device__ __forceinline__ void put(Addr a, int k, uint32_t w) const { a[k] = (uint16_t)w; }
 };
 
 // One step of the model pass: 32 consecutive samples, one per lane (rec = packed record of this lane's sample),
@@ -117,7 +125,7 @@ __device__ __forceinline__ uint32_t model_apply(uint32_t rec, bool valid, const 
     const bool flat = leader && (members & ~plan.zero_mask) == 0 && (row.x & 0xFFu) == 127u;
     if (__any_sync(kFull, flat)) {
         const bool flat_chain = __shfl_sync(kFull, flat, head);          // every lane takes part in the shuffle
-        if (mine && flat_chain) sink.put(off, tab2[127 * 2 + 1]);
+        if (mine && flat_chain) sink.put(sink.at(off), 0, tab2[127 * 2 + 1]);
         if (flat) members = 0;
     }
     const int rounds = __reduce_max_sync(kFull, leader ? __popc(members) : 0);
@@ -133,6 +141,9 @@ __device__ __forceinline__ uint32_t model_apply(uint32_t rec, bool valid, const 
         const uint32_t ma = (uint32_t)abs(md);
         const int me = ma ? 31 - __clz(ma) : -1;
         const int maxe = __reduce_max_sync(kFull, has ? me : -1);
+        // entries of the member: zero flag at +0, exponent at +1 .. +e+1, mantissa at +e+2 .. +2e+1, sign at +2e+2
+        const typename Sink::Addr a0 = sink.at(mo);
+        const typename Sink::Addr ae = a0 + max(me, 0);
 
         // the sub-states are independent of one another: issue every look-up of the straight part first
         const uint32_t w0 = tab2[s0b * 2 + (me < 0)];                                   // ctx 0, :187 / :204
@@ -141,24 +152,28 @@ __device__ __forceinline__ uint32_t model_apply(uint32_t rec, bool valid, const 
         const uint32_t w3 = tab2[s3b * 2 + (me >= 3)];
         const uint32_t w5 = tab2[s5b * 2 + ((ma >> max(me - 1, 0)) & 1u)];             // ctx 5, first mantissa bit
         const uint32_t w7 = tab2[s7b * 2 + (md < 0)];                                   // ctx 7, sign, :200-202
-        if (has) { sink.put(mo, w0); s0b = w0 >> 16; }
+        if (has) { sink.put(a0, 0, w0); s0b = w0 >> 16; }
         if (maxe >= 0) {
             if (has && me >= 0) {
-                sink.put(mo + 1, w1); s1b = w1 >> 16;
-                sink.put(mo + 2 * me + 2, w7); s7b = w7 >> 16;
+                sink.put(a0, 1, w1); s1b = w1 >> 16;
+                sink.put(ae + max(me, 0), 2, w7); s7b = w7 >> 16;
             }
             if (has && me >= 1) {
-                sink.put(mo + 2, w2); s2b = w2 >> 16;
-                sink.put(mo + me + 2, w5); s5b = w5 >> 16;
+                sink.put(a0, 2, w2); s2b = w2 >> 16;
+                sink.put(ae, 2, w5); s5b = w5 >> 16;
             }
-            if (has && me >= 2) { sink.put(mo + 3, w3); s3b = w3 >> 16; }
+            if (has && me >= 2) { sink.put(a0, 3, w3); s3b = w3 >> 16; }
+            typename Sink::Addr a4 = a0;
             for (int j = 0; j <= maxe - 3; ++j) {                                       // ctx 4: positions 4..e+1
                 const uint32_t w4 = tab2[s4b * 2 + (j < me - 3)];
-                if (has && j <= me - 3) { sink.put(mo + 4 + j, w4); s4b = w4 >> 16; }
+                if (has && j <= me - 3) { sink.put(a4, 4, w4); s4b = w4 >> 16; }
+                a4 += 1;
             }
+            typename Sink::Addr a6 = ae;
             for (int j = 0; j <= maxe - 2; ++j) {                                       // ctx 6: mantissa bits e-2..0
                 const uint32_t w6 = tab2[s6b * 2 + ((ma >> max(me - 2 - j, 0)) & 1u)];
-                if (has && j <= me - 2) { sink.put(mo + me + 3 + j, w6); s6b = w6 >> 16; }
+                if (has && j <= me - 2) { sink.put(a6, 3, w6); s6b = w6 >> 16; }
+                a6 += 1;
             }
         }
     }
@@ -474,12 +489,12 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
 
 // ---------------------------------------------------------------------------------------------------
 // K2 fused: records -> slice payload in ONE kernel, no bin queue in HBM.  NS slices per CTA, 1 + 2 NS warps:
-//   model warp   (one per slice) the model pass above, its entries go to a shared-memory FIFO instead of HBM;
+//   model warp   (one per slice) the model pass above, its entries go to a shared-memory FIFO instead of HBM; it
+//                runs to the end of the slice at its own pace, as far ahead as the FIFO has room;
 //   chain warp   (one per CTA) the range recurrence of all NS slices in lock step, 32/NS lanes each;
 //   helper warp  (one per slice) expands FIFO entries to operands for the chain and runs the byte side.
-// They meet at one barrier per 256-decision block.  Before the barrier that ends iteration i the model warp has
-// produced at least (i+3) blocks (or everything); in iteration b the helper expands block b+1, the chain runs
-// block b, the helper turns block b-1 into bytes.  With the state rows behind L1 (kGlobalState) a slice needs
+// Chain and helpers meet at one barrier per 256-decision block: in iteration b the helper turns block b-1 into
+// bytes and expands block b+1 (waiting for the model warp if it has to), the chain runs block b.  With the state rows behind L1 (kGlobalState) a slice needs
 // ~14 KB of shared memory, so every slice of a 1024-image batch is resident at once; with the rows in shared
 // memory (NS = 1, few slices) the CTA takes 79 KB.
 //
@@ -489,19 +504,47 @@ __global__ void __launch_bounds__(128) k_range_pass_ws(const uint16_t* __restric
 // ---------------------------------------------------------------------------------------------------
 constexpr int kBlkF = 256;                                   // decisions per block of the fused coder
 constexpr int kPerLane = kBlkF / 32;                         // helper: consecutive decisions per lane
+#ifndef LLC_SPIN_NS
+#define LLC_SPIN_NS 1024
+#endif
 #ifndef LLC_AHEAD
 #define LLC_AHEAD 3
 #endif
 constexpr int kAhead = LLC_AHEAD;                            // blocks the model warp runs ahead of the chain
 constexpr int kFifoF = kAhead <= 3 ? 2048 : 4096;            // FIFO entries: kAhead blocks + one step (<= 608) fit
 static_assert(kAhead * kBlkF + 32 * 19 + kBlkF <= kFifoF, "the model warp must not overrun the block being expanded");
+// The FIFO is a ring of kFifoF entries followed by kFifoSpill more: the entries of one sample are stored at consecutive
+// addresses from the (wrapped) position of its first decision, so the one sample per lap that straddles the end of the
+// ring spills into the tail, and its lane copies the spilled entries to the start of the ring afterwards.
+constexpr int kFifoSpill = 24;                               // >= 18 (a sample has at most 19 entries), 16-byte multiple
+struct FifoAddr {                                            // shared-window byte address of a 16-bit entry
+    uint32_t a;
+    __device__ __forceinline__ FifoAddr operator+(int k) const { return FifoAddr{a + 2u * (uint32_t)k}; }
+    __device__ __forceinline__ FifoAddr& operator+=(int k) { a += 2u * (uint32_t)k; return *this; }
+};
 struct FifoSink {
     uint32_t fifo_s;     // shared-window address of the FIFO
     uint32_t base;
-    __device__ __forceinline__ void put(uint32_t pos, uint32_t w) const {
-        sts16(fifo_s + (((base + pos) & (kFifoF - 1)) << 1), w);
-    }
+    typedef FifoAddr Addr;
+    __device__ __forceinline__ Addr at(uint32_t pos) const { return FifoAddr{fifo_s + (((base + pos) & (kFifoF - 1)) << 1)}; }
+    __device__ __forceinline__ void put(Addr p, int k, uint32_t w) const { sts16(p.a + 2u * (uint32_t)k, w); }
 };
+// after a step: the lane whose sample crossed the end of the ring brings its spilled entries home
+__device__ __forceinline__ void fifo_unspill(uint32_t fifo_s, uint32_t base, uint32_t off, uint32_t nb, bool valid) {
+    const uint32_t start = (base + off) & (kFifoF - 1);
+    const bool spilled = valid && start + nb > (uint32_t)kFifoF;
+    if (__any_sync(kFull, spilled)) {
+        if (spilled) {
+            const uint32_t n = start + nb - kFifoF;
+            for (uint32_t k = 0; k < n; ++k) {
+                uint16_t v;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fifo_s + 2u * (kFifoF + k)) : "memory");
+                sts16(fifo_s + 2u * k, v);
+            }
+        }
+        __syncwarp();
+    }
+}
 
 // One decision of the range recurrence.  With x = range * M + A (24 bits),
 //   range' = x < 0x10000 ? x & ~0xFF : x >> 8   (RangeEncoder::put + the renormalisation shift, llcomp.hpp:57-73)
@@ -695,9 +738,14 @@ __device__ __forceinline__ int assign_role(int wslot, int lane) {
 // prefers the eligible warp with the highest warp id, so the recurrence warp -- the critical path -- is made the
 // highest-numbered warp of the least populated sub-partition and shares it only with (light) helper warps; the
 // model warps are spread evenly over the other three.
-template <int NS>
+// kAlone: the CTA is launched with 4 ceil(2 NS / 3) warps, so that the model and helper warps fit the other three
+// sub-partitions; the recurrence warp then has a sub-partition to itself (its spare warps leave at once: role -1).
+// Roles: 0 recurrence, 1..NS model, NS+1..2NS helper.
+__host__ __device__ constexpr int fused_warps(int ns, int mode) { return mode == 2 ? 4 * ((2 * ns + 2) / 3) : 1 + 2 * ns; }
+template <int NS, bool kAlone>
 __device__ __forceinline__ int assign_role_solo(int wslot, int lane) {
-    constexpr int kWarps = 1 + 2 * NS;
+    constexpr int kWarps = fused_warps(NS, kAlone ? 2 : 1);
+    constexpr int kRoles = 2 * NS;
     __shared__ uint32_t s_wid[kWarps];
     uint32_t wid;
     asm("mov.u32 %0, %%warpid;" : "=r"(wid));
@@ -721,6 +769,7 @@ __device__ __forceinline__ int assign_role_solo(int wslot, int lane) {
     if (wslot == chain) return 0;
     const uint32_t mine = s_wid[wslot];
     const bool on_c = (mine & 3u) == (uint32_t)c;
+    if (kAlone && on_c) return -1;
     // order of the warps off the chain's sub-partition: by rank inside their sub-partition, then by sub-partition
     auto key_of = [&](int w) -> uint32_t {
         uint32_t rank = 0;
@@ -737,17 +786,25 @@ __device__ __forceinline__ int assign_role_solo(int wslot, int lane) {
         off_c += !w_on_c;
         if (w_on_c == on_c && key_of(w) < my_key) ++before;
     }
-    if (!on_c) return before < NS ? 1 + before : 1 + NS + (before - NS);
-    return 1 + NS + (off_c - NS) + before;
+    // models first (off the recurrence's sub-partition), then the helpers
+    const int idx = on_c ? off_c + before : before;
+    return idx < kRoles ? 1 + idx : -1;
 }
 
-constexpr int kFusedPerSlice = kFifoF * 2 + 2 * kRingSlots * 16 + 2 * kBlkF * 4 + 32;   // + control words
-constexpr int fused_smem_bytes(int ns, bool global_state) {
-    return 1024 + ns * kFusedPerSlice + (global_state ? 0 : kRowBytesSmem);
+constexpr int kFifoBytes = (kFifoF + kFifoSpill) * 2;
+constexpr int kFusedPerSlice = kFifoBytes + 2 * kRingSlots * 16 + 2 * kBlkF * 4 + 64;   // + control words
+// kPixels (the CTA computes its records from the pixels, no record array in HBM): a ring of four chunks of 32 pixels x
+// <= 4 planes of records per slice, and the quantiser tables once per CTA
+constexpr int kRecChunk = 32 * 4;
+constexpr int kRecRing = 4;
+constexpr int kRecBytes = kRecRing * kRecChunk * 4;
+constexpr int fused_smem_bytes(int ns, bool global_state, bool pixels) {
+    return 1024 + ns * kFusedPerSlice + (global_state ? 0 : kRowBytesSmem) + (pixels ? ns * kRecBytes + (int)sizeof(QuantBytes) : 0);
 }
 
-template <int NS, bool kGlobalState, bool kSolo>
-__global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const uint32_t* __restrict__ sym, Geom g,
+template <int NS, bool kGlobalState, int kSolo, bool kPixels>
+__global__ void __launch_bounds__(32 * fused_warps(NS, kSolo)) k_slice_coder_fused(const uint32_t* __restrict__ sym,
+                                                                       const uint8_t* __restrict__ pixels, Geom g,
                                                                        uint8_t* __restrict__ scratch,
                                                                        uint32_t* __restrict__ slice_bytes,
                                                                        int* __restrict__ status,
@@ -759,20 +816,27 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
     uint32_t* tab2 = reinterpret_cast<uint32_t*>(smem);
     auto slice_smem = [&](int q) { return smem + 1024 + q * kFusedPerSlice; };
     auto fifo_of = [&](int q) { return reinterpret_cast<uint16_t*>(slice_smem(q)); };
-    auto ring_of = [&](int q, int buf) { return reinterpret_cast<uint4*>(slice_smem(q) + kFifoF * 2) + buf * kRingSlots; };
+    auto ring_of = [&](int q, int buf) { return reinterpret_cast<uint4*>(slice_smem(q) + kFifoBytes) + buf * kRingSlots; };
     auto x_of = [&](int q, int buf) {
-        return reinterpret_cast<uint32_t*>(slice_smem(q) + kFifoF * 2 + 2 * kRingSlots * 16) + buf * kBlkF;
+        return reinterpret_cast<uint32_t*>(slice_smem(q) + kFifoBytes + 2 * kRingSlots * 16) + buf * kBlkF;
     };
-    // per slice, per iteration parity: decisions that exist from block b on, as the model warp knew before the
-    // barrier that started iteration b (kUnbounded while it has not reached the end of the slice)
-    constexpr int kUnbounded = 1 << 30;
+    // Flow control between the roles of a slice: shared-memory words with one writer each.
+    //   ctl[0]          model -> helper         decisions produced so far (mod 2^32)
+    //   ctl[2]          model -> helper         1 once the model warp has reached the end of the slice
+    //   ctl[1]          helper -> model         FIFO positions below this one are expanded and may be overwritten
+    //   ctl[4 + (b&3)]  helper -> chain/helper  decisions of block b of the slice (<= 0: none)
+    // The model warp runs to the end of its slice at its own pace, as far ahead as the FIFO has room; only the chain
+    // warp and the helpers meet at a barrier per block.  (With one CTA barrier for all roles every iteration took as
+    // long as its slowest warp -- a model warp that met an L2 miss -- although the FIFO still held blocks of slack:
+    // per-role counters showed every role under 75 % busy at seven slices per CTA.)
     auto ctl_of = [&](int q) {
-        return reinterpret_cast<volatile int*>(slice_smem(q) + kFifoF * 2 + 2 * kRingSlots * 16 + 2 * kBlkF * 4);
+        return reinterpret_cast<volatile uint32_t*>(slice_smem(q) + kFifoBytes + 2 * kRingSlots * 16 + 2 * kBlkF * 4);
     };
+    auto role_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(32 * (1 + NS)) : "memory"); };
 
     const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
     // 0 chain, 1..NS model, NS+1..2NS helper
-    const int role = kSolo ? assign_role_solo<NS>(wslot, lane) : assign_role<NS>(wslot, lane);
+    const int role = kSolo ? assign_role_solo<NS, kSolo == 2>(wslot, lane) : assign_role<NS>(wslot, lane);
     // slice (within the CTA) this warp / lane group serves; spare chain lanes shadow the last slice
     const int q = role == 0 ? min(lane / L, NS - 1) : (role - 1) % NS;
     const uint32_t sidx = blockIdx.x * NS + q;
@@ -783,43 +847,122 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
     const uint64_t n = live ? sl.n : 0;
     uint2* state = kGlobalState ? gstate + (size_t)s * kContexts
                                 : reinterpret_cast<uint2*>(smem + 1024 + NS * kFusedPerSlice);
+    uint8_t* const px_smem = smem + 1024 + NS * kFusedPerSlice + (kGlobalState ? 0 : kRowBytesSmem);
+    QuantBytes* const quant = reinterpret_cast<QuantBytes*>(px_smem + NS * kRecBytes);
     uint16_t* fifo = fifo_of(q);
-    volatile int* ctl = ctl_of(q);
+    volatile uint32_t* ctl = ctl_of(q);
 
     if (role == 0) fill_tab2(tab2, lane);
+    if (kPixels)
+        for (int i = threadIdx.x; i < (int)(sizeof(QuantBytes) / 16); i += blockDim.x)
+            reinterpret_cast<uint4*>(quant)[i] = reinterpret_cast<const uint4*>(&c_quant_bytes_coder)[i];
+    if (role > NS && lane < 16) ctl[lane] = 0;
+    const bool spare = role < 0;
     if (!kGlobalState)
         for (int i = threadIdx.x; i < kRowBytesSmem / 16; i += blockDim.x)
             reinterpret_cast<uint4*>(state)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    if (spare) return;
 
     const bool is_model = role >= 1 && role <= NS, is_helper = role > NS;
+    // kPixels: the front end runs inside the CTA, in the model warp.  Records are made 32 pixels at a time (lane = pixel,
+    // all its planes, any position of the slice: records_of_pixel) into a ring of chunks in shared memory, from which
+    // the steps read them two steps ahead, as they read the record array otherwise.  (Measured on configs[3], seven
+    // slices per CTA, against 176 + 4 ms with K1 and the record array: 193 ms this way; 210 ms with the helper warp
+    // making the records before its barrier -- its global loads then delay the recurrence warp; 270 ms with one
+    // producer warp for the seven slices of the CTA -- it cannot keep up.)
+    const int C = g.C;                                        // 3 or 4 with kPixels (the launcher checks)
+    const size_t pitch = (size_t)g.W * C;
+    const uint8_t* const sl_px = kPixels ? pixels + ((size_t)sl.img * g.H + sl.y0) * pitch + (size_t)sl.x0 * C : nullptr;
+    const uint32_t n_px = live ? (uint32_t)sl.w * (uint32_t)sl.h : 0u;
+    uint32_t* const recbuf = reinterpret_cast<uint32_t*>(px_smem + q * kRecBytes);
+    auto produce = [&](uint32_t chunk) {
+        const int8_t* const q11 = quant->q11 + kQB;
+        const int8_t* const q5 = quant->q5 + kQB;
+        const uint32_t pi = chunk * 32u + lane;
+        if (pi < n_px) {
+            const uint32_t y = pi / (uint32_t)sl.w, x = pi - y * (uint32_t)sl.w;
+            const uint8_t* p = sl_px + y * pitch + (size_t)x * C;
+            uint32_t* dst = recbuf + (chunk & (kRecRing - 1)) * kRecChunk + lane * C;
+            if (C == 3) {
+                uint32_t r[3];
+                records_of_pixel<3>(p, pitch, (int)x, (int)y, sl.w, q11, q5, r);
+                dst[0] = r[0]; dst[1] = r[1]; dst[2] = r[2];
+            } else {
+                uint32_t r[4];
+                records_of_pixel<4>(p, pitch, (int)x, (int)y, sl.w, q11, q5, r);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+            if (x + 32u < (uint32_t)sl.w) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32 * C));
+        }
+        __syncwarp();
+    };
+
     // ---- model warp: software pipeline over 32-sample steps.  Records two steps ahead; the plan (votes, match)
     // and an L1 prefetch of the state rows one step ahead: a working set of 8 slices x ~4000 live rows does not
     // fit L1, and a row fetched from L2 in the middle of a step costs ~700 cycles of a warp with nothing else to do.
-    uint64_t base = 0, produced = 0;
-    uint32_t rec_cur = (is_model && lane < n) ? in[lane] : 0u;
-    uint32_t rec_next = (is_model && 32 + lane < n) ? in[32 + lane] : 0u;
-    StepPlan plan_cur = {0, 0, 0, 0};
-    if (is_model) plan_cur = model_plan(rec_cur, lane < n, lane);
-    auto produce_until = [&](uint64_t target, uint32_t for_iter) {
-        while (base < n && produced < target) {
+    if (is_model) {
+#ifdef LLC_ROLE_TIMING
+        long long t_spin = 0, t_all0 = clock64();
+#endif
+        uint64_t base = 0;
+        uint32_t produced = 0, cons_seen = 0;                 // positions mod 2^32: the roles are never a ring apart
+        uint32_t rec_seen = 0;                                // kPixels: chunks made so far
+        // record of this lane's sample in step k (32 samples per step; a step never straddles two chunks)
+        auto step_record = [&](uint64_t k) -> uint32_t {
+            const uint64_t first = k * 32u;
+            if (!kPixels) return first + lane < n ? in[first + lane] : 0u;
+            if (first >= n) return 0u;
+            const uint32_t chunk = (uint32_t)(k / (uint32_t)C), sub = (uint32_t)(k - (uint64_t)chunk * C);
+            while (rec_seen <= chunk) produce(rec_seen++);    // (a chunk two back is in registers by now: ring of four)
+            return first + lane < n ? recbuf[(chunk & (kRecRing - 1)) * kRecChunk + sub * 32u + lane] : 0u;
+        };
+        uint32_t rec_cur = step_record(0);
+        uint32_t rec_next = step_record(1);
+        StepPlan plan_cur = model_plan(rec_cur, lane < n, lane);
+        while (base < n) {
+            if (produced - cons_seen + 32 * 19 > (uint32_t)kFifoF) {       // no room for a whole step: wait for the helper
+#ifdef LLC_ROLE_TIMING
+                const long long t_in = clock64();
+#endif
+                // (room comes a block at a time, every ~5000 cycles; polling faster only takes issue slots from the
+                // recurrence warp: with 256 ns sleeps the seven model warps of a CTA spent more instructions polling
+                // than the whole CTA spent working)
+                while (produced - (cons_seen = ctl[1]) + 32 * 19 > (uint32_t)kFifoF) __nanosleep(LLC_SPIN_NS);
+#ifdef LLC_ROLE_TIMING
+                t_spin += clock64() - t_in;
+#endif
+            }
             const bool valid = base + lane < n, valid_next = base + 32 + lane < n;
-            const uint64_t k = base + 64 + lane;
-            const uint32_t rec_after = k < n ? in[k] : 0u;
+            const uint32_t rec_after = step_record(base / 32 + 2);
             // this step's rows first: their latency (L1, often L2) runs under the votes and the match of the next step
             const uint2 row = model_row(rec_cur, valid, plan_cur, state, lane);
             if (kGlobalState && valid_next) asm volatile("prefetch.global.L1 [%0];" ::"l"(state + (rec_next >> 11)));
             const StepPlan plan_next = model_plan(rec_next, valid_next, lane);
-            produced += model_apply(rec_cur, valid, plan_cur, row, state, tab2, lane, FifoSink{smem_addr(fifo), (uint32_t)produced});
+            model_apply(rec_cur, valid, plan_cur, row, state, tab2, lane, FifoSink{smem_addr(fifo), produced});
+            {
+                const uint32_t a_cur = (uint32_t)abs(residual_of(rec_cur));
+                fifo_unspill(smem_addr(fifo), produced, plan_cur.off, valid ? (a_cur ? 65u - 2u * __clz(a_cur) : 1u) : 0u, valid);
+            }
+            produced += plan_cur.total;
             rec_cur = rec_next; rec_next = rec_after; plan_cur = plan_next;
             base += 32;
-        }
-        if (lane == 0) {
-            const long long left = (long long)produced - (long long)for_iter * kBlkF;
-            ctl[for_iter & 1] = base < n ? kUnbounded : (int)max(-(long long)kUnbounded, min((long long)kUnbounded, left));
+            __syncwarp();                                     // every lane's entries before the count
+            if (lane == 0) { __threadfence_block(); ctl[0] = produced; }
         }
         __syncwarp();
-    };
+        if (lane == 0) { __threadfence_block(); ctl[2] = 1u; }
+#ifdef LLC_ROLE_TIMING
+        if (lane == 0) {
+            uint32_t smid, wid;
+            asm("mov.u32 %0, %%smid;" : "=r"(smid));
+            asm("mov.u32 %0, %%warpid;" : "=r"(wid));
+            const long long tot = clock64() - t_all0;
+            printf("cta %d sm %u role %d work %lld total %lld wid %u\n", blockIdx.x, smid, role, tot - t_spin, tot, wid);
+        }
+#endif
+        return;                                               // the other roles meet at a named barrier that does not count this warp
+    }
     // ---- helper warp
     uint8_t* const out0 = scratch + scratch_off(sl, s);
     uint8_t* const out_end = out0 + scratch_cap(sl);
@@ -862,10 +1005,25 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
     const uint32_t two8 = c_two8;
 #endif
 
-    if (is_model) produce_until(kAhead * kBlkF, 0);
-    __syncthreads();
-    if (is_helper) nd_cur = expand(0);
-    __syncthreads();
+    // decisions of block blk once the model warp has produced all of it (256), or what is left of the slice (<= 0: none)
+    auto wait_block = [&](uint32_t blk) -> int {
+        const uint32_t first = blk * (uint32_t)kBlkF;
+        for (;;) {
+            const uint32_t done = ctl[2];
+            const int ahead = (int)(ctl[0] - first);          // read after the flag: the last count precedes it
+            if (ahead >= kBlkF) return kBlkF;
+            if (done) return ahead;
+            __nanosleep(128);
+        }
+    };
+    if (is_helper) {
+        const int c0 = wait_block(0);
+        __threadfence_block();
+        nd_cur = c0 > 0 ? expand(0) : 0u;
+        __syncwarp();
+        if (lane == 0) { ctl[1] = (uint32_t)kBlkF; ctl[4] = (uint32_t)c0; ctl[7] = 0u; }
+    }
+    role_sync();
 
 #ifdef LLC_ROLE_TIMING
     long long t_work = 0, t_all0 = clock64();
@@ -874,16 +1032,14 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
 #ifdef LLC_ROLE_TIMING
         const long long t_in = clock64();
 #endif
-        // decisions of block k of slice qq that exist (<= 0: none); identical in every warp
-        int max_left = -kUnbounded;                          // decisions from block b on, longest slice of the CTA
+        // decisions of blocks b and b-1, longest slice of the CTA; identical in every warp
+        int max_cur = -1, max_prev = -1;
 #pragma unroll
-        for (int qq = 0; qq < NS; ++qq) max_left = max(max_left, ctl_of(qq)[b & 1]);
-        const int my_left = ctl[b & 1];                      // ... and of this warp's slice (model, helper)
-        auto block_count = [&](int rel) -> int {             // decisions of block b + rel of this warp's slice
-            return min(kBlkF, my_left - rel * kBlkF);
-        };
-        const int max_cur = min(kBlkF, max_left);
-        if (max_cur <= 0 && (b == 0 || max_left + kBlkF <= 0)) break;   // nothing in block b nor in block b-1
+        for (int qq = 0; qq < NS; ++qq) {
+            max_cur = max(max_cur, (int)ctl_of(qq)[4 + (b & 3)]);
+            max_prev = max(max_prev, (int)ctl_of(qq)[4 + ((b + 3) & 3)]);
+        }
+        if (max_cur <= 0 && (b == 0 || max_prev <= 0)) break;            // nothing in block b nor in block b-1
 
         if (role == 0) {
             if (max_cur > 0) {
@@ -893,40 +1049,45 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
                 uint4* xo = reinterpret_cast<uint4*>(x_of(q, b & 1));
                 const int trips = (max_cur + 7) / 8;
                 uint4 a0 = rp[0], a1 = rp[32], a2 = rp[64], a3 = rp[96];
+                // x of a group of four is stored one decision late: a store issued right behind the multiply-add that
+                // produces its last word waits for it, and the in-order warp with it (profiles/microbench/chain_lat.cu:
+                // 16.8 -> 15.8 cycles per decision; 14.9 without any store)
+                uint4 xs, xw = make_uint4(0, 0, 0, 0);
                 for (int v = 0; v < trips; ++v) {
                     const uint4 b0 = rp[128], b1 = rp[160], b2 = rp[192], b3 = rp[224];
-                    uint4 xs;
                     xs.x = yc = chain_step(yc, a0, two8);
+                    if (v) xo[-1] = xw;
                     xs.y = yc = chain_step(yc, a1, two8);
                     xs.z = yc = chain_step(yc, a2, two8);
                     xs.w = yc = chain_step(yc, a3, two8);
-                    xo[0] = xs;
                     ++rp;
                     a0 = rp[0]; a1 = rp[32]; a2 = rp[64]; a3 = rp[96];
-                    xs.x = yc = chain_step(yc, b0, two8);
-                    xs.y = yc = chain_step(yc, b1, two8);
-                    xs.z = yc = chain_step(yc, b2, two8);
-                    xs.w = yc = chain_step(yc, b3, two8);
-                    xo[1] = xs;
+                    xw.x = yc = chain_step(yc, b0, two8);
+                    xo[0] = xs;
+                    xw.y = yc = chain_step(yc, b1, two8);
+                    xw.z = yc = chain_step(yc, b2, two8);
+                    xw.w = yc = chain_step(yc, b3, two8);
                     xo += 2;
                 }
+                xo[-1] = xw;
             }
-        } else if (is_model) {
-            produce_until((uint64_t)(b + 1 + kAhead) * kBlkF, b + 1);
         } else {
-            const int cnt_prev = b > 0 ? block_count(-1) : 0;
-            const int cnt_next = block_count(1);
+            const int cnt_prev = b > 0 ? (int)ctl[4 + ((b + 3) & 3)] : 0;
             if (cnt_prev > 0)
                 byte_side_lanes(t, overflow, x_carry, x_of(q, (b - 1) & 1),
                                 reinterpret_cast<uint32_t*>(ring_of(q, (b - 1) & 1)), nd_prev, (uint32_t)cnt_prev, lane,
                                 out0, out_end);
             nd_prev = nd_cur;
+            const int cnt_next = wait_block(b + 1);
+            __threadfence_block();
             nd_cur = cnt_next > 0 ? expand(b + 1) : 0u;
+            __syncwarp();
+            if (lane == 0) { ctl[1] = (b + 2) * (uint32_t)kBlkF; ctl[4 + ((b + 1) & 3)] = (uint32_t)cnt_next; }
         }
 #ifdef LLC_ROLE_TIMING
         t_work += clock64() - t_in;
 #endif
-        __syncthreads();
+        role_sync();
     }
 #ifdef LLC_ROLE_TIMING                                       // per-role busy cycles
     if (lane == 0) {
@@ -950,29 +1111,6 @@ __global__ void __launch_bounds__(32 * (1 + 2 * NS)) k_slice_coder_fused(const u
     }
 }
 
-// The fused CTA with the state rows in shared memory takes 79 KB: 2 per SM.  Beyond 2 x 148 slices the rows go
-// behind L1 so that the whole launch is resident at once.
-uint64_t fused_global_state_bytes(uint64_t n_slices) {
-    if (switches().model_smem_state) return 0;
-    // (a forced slices-per-CTA count implies the rows behind L1: the shared-memory form is one slice per CTA)
-    return (n_slices > 2 * 148 || switches().fused_ns) ? n_slices * (uint64_t)kStateBytes : 0;
-}
-
-// (Measured and dropped: asking for a smaller shared-memory carve-out so that the rows behind L1 get more of it.
-// The default carve-out leaves them a 35% L1 hit rate, but the model warp hides that behind its look-ahead and the
-// kernel time did not move, while co-resident launches of a pipelined batch got slower.)
-template <int NS, bool kGlobalState, bool kSolo>
-static cudaError_t launch_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
-                                int* d_status, uint2* gs, unsigned n, cudaStream_t st) {
-    static cudaError_t configured = cudaFuncSetAttribute(k_slice_coder_fused<NS, kGlobalState, kSolo>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         fused_smem_bytes(NS, kGlobalState));
-    if (configured != cudaSuccess) return configured;
-    k_slice_coder_fused<NS, kGlobalState, kSolo><<<(n + NS - 1) / NS, 32 * (1 + 2 * NS), fused_smem_bytes(NS, kGlobalState), st>>>(
-        d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n);
-    return cudaGetLastError();
-}
-
 static int sm_count() {
     static const int n = [] {
         int dev = 0, v = 0;
@@ -983,30 +1121,100 @@ static int sm_count() {
     return n;
 }
 
-cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
-                                     int* d_status, uint8_t* d_gstate, cudaStream_t st) {
+// The fused CTA with the state rows in shared memory takes 79 KB.  While every slice can have an SM of its own the rows
+// stay there; beyond that they go behind L1 and one CTA per SM serves several slices (two such CTAs on an SM measured
+// 162 ms per 1024^2 RGB slice against 150 ms for one CTA with two slices and the rows behind L1).
+uint64_t fused_global_state_bytes(uint64_t n_slices) {
+    if (switches().model_smem_state) return 0;
+    // (a forced slices-per-CTA count implies the rows behind L1: the shared-memory form is one slice per CTA)
+    return (n_slices > (uint64_t)sm_count() || switches().fused_ns) ? n_slices * (uint64_t)kStateBytes : 0;
+}
+
+// (Measured and dropped: asking for a smaller shared-memory carve-out so that the rows behind L1 get more of it.
+// The default carve-out leaves them a 35% L1 hit rate, but the model warp hides that behind its look-ahead and the
+// kernel time did not move, while co-resident launches of a pipelined batch got slower.)
+template <int NS, bool kGlobalState, int kSolo, bool kPixels>
+static cudaError_t launch_fused_from(const uint32_t* d_sym, const uint8_t* d_pixels, const Geom& g, uint8_t* d_scratch,
+                                     uint32_t* d_slice_bytes, int* d_status, uint2* gs, unsigned n, cudaStream_t st) {
+    constexpr int kSmem = fused_smem_bytes(NS, kGlobalState, kPixels);
+    static cudaError_t configured = cudaFuncSetAttribute(k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (configured != cudaSuccess) return configured;
+    k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels><<<(n + NS - 1) / NS, 32 * fused_warps(NS, kSolo), kSmem, st>>>(
+        d_sym, d_pixels, g, d_scratch, d_slice_bytes, d_status, gs, n);
+    return cudaGetLastError();
+}
+
+// The default forms exist twice: reading K1's record array (d_pixels == nullptr) or the pixels themselves.
+struct FusedArgs {
+    const uint32_t* d_sym; const uint8_t* d_pixels; const Geom& g; uint8_t* d_scratch; uint32_t* d_slice_bytes;
+    int* d_status; uint2* gs; unsigned n; cudaStream_t st;
+};
+template <int NS, bool kGlobalState, int kSolo>
+static cudaError_t launch_fused(const FusedArgs& a) {
+    if (a.d_pixels)
+        return launch_fused_from<NS, kGlobalState, kSolo, true>(nullptr, a.d_pixels, a.g, a.d_scratch, a.d_slice_bytes, a.d_status, a.gs, a.n, a.st);
+    return launch_fused_from<NS, kGlobalState, kSolo, false>(a.d_sym, nullptr, a.g, a.d_scratch, a.d_slice_bytes, a.d_status, a.gs, a.n, a.st);
+}
+template <int NS, bool kGlobalState, int kSolo>
+static cudaError_t launch_fused_records(const FusedArgs& a) {     // round-1 arrangements: record array only
+    if (a.d_pixels) return cudaErrorInvalidValue;
+    return launch_fused_from<NS, kGlobalState, kSolo, false>(a.d_sym, nullptr, a.g, a.d_scratch, a.d_slice_bytes, a.d_status, a.gs, a.n, a.st);
+}
+
+
+// true when the fused coder can compute its records from the pixels of this geometry itself (else: K1 + record array)
+bool fused_coder_can_take_pixels(const Geom& g) {
+    return (g.C == 3 || g.C == 4) && (switches().fused_ns == 0 || switches().fused_ns >= 10);
+}
+// Records from the pixels cost time (measured on 1024^2 RGB slices, K1 + record array against pixels: 138.4 / 140.3 ms
+// at one slice per SM, 142.5 / 155.0 at two, 156.5 / 187.0 at four, 181.0 / 199.4 at seven), because the model warp that
+// makes them is the second-busiest role of the CTA; they save the 4-byte-per-sample record array and its 8 bytes per
+// sample of HBM traffic.  So the default takes K1's records while the array fits and the pixels when it does not.
+bool fused_coder_takes_pixels(const Geom& g, bool record_array_fits) {
+    if (!fused_coder_can_take_pixels(g) || switches().coder_records) return false;
+    return switches().coder_pixels || !record_array_fits;
+}
+
+cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const uint8_t* d_pixels, const Geom& g, uint8_t* d_scratch,
+                                     uint32_t* d_slice_bytes, int* d_status, uint8_t* d_gstate, cudaStream_t st,
+                                     uint64_t n_concurrent) {
     const uint64_t ns = g.n_slices();
-    if (ns == 0 || ns > 0x0FFFFFFFull) return cudaErrorInvalidValue;
+    if (ns == 0 || ns > 0x0FFFFFFFull || (d_sym == nullptr) == (d_pixels == nullptr)) return cudaErrorInvalidValue;
+    if (d_pixels && !fused_coder_can_take_pixels(g)) return cudaErrorInvalidValue;
     const unsigned n = (unsigned)ns;
-    if (!d_gstate) return launch_fused<1, false, false>(d_sym, g, d_scratch, d_slice_bytes, d_status, nullptr, n, st);
+    if (!d_gstate) return launch_fused<1, false, 2>(FusedArgs{d_sym, d_pixels, g, d_scratch, d_slice_bytes, d_status, nullptr, n, st});
     // the caller decides where the rows live (fused_global_state_bytes); all states start at 0
     cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);
     if (e != cudaSuccess) return e;
     // One CTA per SM, as few slices per CTA as one wave allows (1024 slices on 148 SMs: 7); beyond 7 per SM the
-    // launch takes several waves.  LLCOMP_FUSED_NS=1|2|4 selects the older arrangement (several CTAs per SM, roles
-    // dealt by arrival order on the SM) that the default is tested against; 13..17 forces the solo form with 3..7.
-    int per_cta = 10 + min(7, max(3, (int)((n + sm_count() - 1) / sm_count())));
+    // launch takes several waves.  Up to five slices per CTA the recurrence warp gets a sub-partition of its own
+    // (20+: measured 154 against 160 ms at four per SM); with six or seven the model warps would then be too crowded on
+    // the other three (no gain at seven), so it shares its sub-partition with two helper warps (10+).
+    // LLCOMP_FUSED_NS=1|2|4 selects the round-1 arrangement (several CTAs per SM, roles dealt by arrival order on the
+    // SM) that the default is tested against; 11..17 and 22..27 force a solo form.
+    const uint64_t n_resident = std::max<uint64_t>(n, n_concurrent);
+    const int per_sm = (int)std::min<uint64_t>(7, std::max<uint64_t>(2, (n_resident + sm_count() - 1) / sm_count()));
+    int per_cta = (per_sm <= 5 ? 20 : 10) + per_sm;
     if (switches().fused_ns) per_cta = switches().fused_ns;
     uint2* gs = reinterpret_cast<uint2*>(d_gstate);
+    const FusedArgs a{d_sym, d_pixels, g, d_scratch, d_slice_bytes, d_status, gs, n, st};
     switch (per_cta) {
-        case 1: return launch_fused<1, true, false>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-        case 2: return launch_fused<2, true, false>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-        case 4: return launch_fused<4, true, false>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-        case 13: return launch_fused<3, true, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-        case 14: return launch_fused<4, true, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-        case 15: return launch_fused<5, true, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-        case 16: return launch_fused<6, true, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
-        case 17: return launch_fused<7, true, true>(d_sym, g, d_scratch, d_slice_bytes, d_status, gs, n, st);
+        case 1: return launch_fused_records<1, true, 0>(a);
+        case 2: return launch_fused_records<2, true, 0>(a);
+        case 4: return launch_fused_records<4, true, 0>(a);
+        case 11: return launch_fused<1, true, 1>(a);
+        case 12: return launch_fused<2, true, 1>(a);
+        case 13: return launch_fused<3, true, 1>(a);
+        case 14: return launch_fused<4, true, 1>(a);
+        case 15: return launch_fused<5, true, 1>(a);
+        case 16: return launch_fused<6, true, 1>(a);
+        case 17: return launch_fused<7, true, 1>(a);
+        case 22: return launch_fused<2, true, 2>(a);
+        case 23: return launch_fused<3, true, 2>(a);
+        case 24: return launch_fused<4, true, 2>(a);
+        case 25: return launch_fused<5, true, 2>(a);
+        case 27: return launch_fused<7, true, 2>(a);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -17,29 +17,18 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sample.cuh"
 
 namespace llc {
 
 namespace {
 
 constexpr int kFrThreads = 128;
-constexpr int kFrRows = 32;
-constexpr int kQB = 640;                                    // plane differences lie in [-637, 637]
-
-struct QuantBytes {
-    int8_t q11[2 * kQB];
-    int8_t q5[2 * kQB];
-};
-constexpr QuantBytes make_quant_bytes() {
-    QuantBytes t{};
-    for (int i = 0; i < 2 * kQB; ++i) {
-        const int x = i - kQB, a = x < 0 ? -x : x;
-        const int m11 = (a >= 1) + (a >= 2) + (a >= 5) + (a >= 12) + (a >= 35), m5 = (a >= 1) + (a >= 4);
-        t.q11[i] = (int8_t)(x < 0 ? -m11 : m11);              // quant11_table, llcomp.hpp:316-333 (closed form)
-        t.q5[i] = (int8_t)(x < 0 ? -m5 : m5);                 // quant5_table,  llcomp.hpp:297-314
-    }
-    return t;
-}
+#ifndef LLC_FR_PX3
+#define LLC_FR_PX3 8
+#define LLC_FR_ROWS3 16
+#define LLC_FR_MINB3 3
+#endif
 __constant__ QuantBytes c_quant_bytes = make_quant_bytes();
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,26 +60,6 @@ __device__ __forceinline__ void tma_row(uint32_t dst, const void* src, uint32_t 
                  "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// One sample from its seven plane values (all neighbours already substituted): llcomp.hpp:424-436.
-// d2 is taken as t - tl, so that the predictor's l + t - tl is l + d2; q11 is odd, hence the -11.
-__device__ __forceinline__ uint32_t code_sample(int cur, int l, int L, int tl, int t, int tr, int n5,
-                                                const int8_t* __restrict__ q11, const int8_t* __restrict__ q5) {
-    const int d1 = l - tl, d2 = t - tl, d3 = t - tr, d4 = L - l;
-    int hash = (q11[d3] * 11 - q11[d2]) * 11 + q11[d1] + 605 * q5[d4] + n5;    // :424-429 (n5 = 3025 q5(T - t))
-    const int hi = max(l, t), lo = min(l, t);
-    const int pred = max(min(l + d2, hi), lo);                                    // median(l, l+t-tl, t), :430
-    int diff = cur - pred;                                                        // :431
-    const int s = hash >> 31;                                                     // :433-436
-    hash = abs(hash);
-    diff = (diff ^ s) - s;
-    return ((uint32_t)hash << 11) | ((uint32_t)diff & 0x7FFu);
-}
-
-template <int CT>
-struct Px {
-    int v[CT];
-};
-
 // Planes of the pixel whose first byte is local byte k of the word array (llcomp.hpp:396-409).
 template <int CT, int NW>
 __device__ __forceinline__ Px<CT> planes_at(const uint32_t (&w)[NW], int k) {
@@ -106,45 +75,47 @@ __device__ __forceinline__ Px<CT> planes_at(const uint32_t (&w)[NW], int k) {
     return p;
 }
 
-template <int CT, int PX>
+template <int CT, int PX, int ROWS>
 struct FrShape {
     static constexpr int kRegionW = kFrThreads * PX;           // pixels of a region row
     static constexpr int kRowBytes = kRegionW * CT + 32;       // + one 16-byte chunk either side
-    static constexpr int kRawBytes = (kFrRows + 2) * kRowBytes;
-    static constexpr int kSmem = kRawBytes + (int)sizeof(QuantBytes) + 16;
+    static constexpr int kSmem = (ROWS + 2) * kRowBytes;       // dynamic: the raw rows (tables and barrier are static)
     // bytes a thread reads per row: pixels x-2 .. x+PX, starting at the word that holds byte 16 - 2 CT + PX CT tid
     static constexpr int kShift = (16 - 2 * CT) & 3;
     static constexpr int kWords = (kShift + (PX + 3) * CT + 3) / 4;
     static_assert((PX * CT) % 4 == 0, "a thread's pixel group starts on a word");
+    static_assert(ROWS % 2 == 0, "the row loop is unrolled by two");
 };
 
-template <int CT, int PX>
-__global__ void __launch_bounds__(kFrThreads, 4) k_frontend_rows(const uint8_t* __restrict__ pixels, Geom g,
-                                                                 uint32_t* __restrict__ sym) {
-    using S = FrShape<CT, PX>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* raw = smem;
-    QuantBytes* lut = reinterpret_cast<QuantBytes*>(smem + S::kRawBytes);
-    const uint32_t bar = smem_u32(smem + S::kRawBytes + sizeof(QuantBytes));
+template <int CT, int PX, int ROWS, int MINB>
+__global__ void __launch_bounds__(kFrThreads, MINB) k_frontend_rows(const uint8_t* __restrict__ pixels, Geom g,
+                                                                    uint32_t* __restrict__ sym) {
+    using S = FrShape<CT, PX, ROWS>;
+    extern __shared__ __align__(128) uint8_t raw[];
+    // static, so that a look-up is one LDS whose table address is an immediate: the difference that indexes it then
+    // comes straight from the multiply-add pipe instead of a three-input add on the (busier) ALU pipe
+    __shared__ __align__(16) QuantBytes lut;
+    __shared__ __align__(8) unsigned long long bar_word;
+    const uint32_t bar = smem_u32(&bar_word);
 
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
-    const int rx0 = blockIdx.x * S::kRegionW, ry0 = blockIdx.y * kFrRows;
+    const int rx0 = blockIdx.x * S::kRegionW, ry0 = blockIdx.y * ROWS;
     const size_t pitch = (size_t)g.W * CT;
     const uint8_t* base = pixels + (size_t)img * g.H * pitch;
 
-    // ---- rows ry0-2 .. ry0+kFrRows-1 of the region -> shared memory, by the TMA unit
+    // ---- rows ry0-2 .. ry0+ROWS-1 of the region -> shared memory, by the TMA unit
     const bool pre = rx0 > 0, post = rx0 + S::kRegionW < g.W;
     const uint32_t row_bytes = (uint32_t)(min(S::kRegionW, g.W - rx0) * CT) + (pre ? 16u : 0u) + (post ? 16u : 0u);
     const int r_first = max(0, 2 - ry0);                                   // rows above the image do not exist
-    const int r_end = min(kFrRows + 2, g.H - ry0 + 2);
+    const int r_end = min(ROWS + 2, g.H - ry0 + 2);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bar, row_bytes * (uint32_t)(r_end - r_first));
     }
     for (int i = tid; i < (int)(sizeof(QuantBytes) / 16); i += kFrThreads)
-        reinterpret_cast<uint4*>(lut)[i] = reinterpret_cast<const uint4*>(&c_quant_bytes)[i];
+        reinterpret_cast<uint4*>(&lut)[i] = reinterpret_cast<const uint4*>(&c_quant_bytes)[i];
     __syncthreads();
     if (tid >= r_first && tid < r_end) {
         const uint8_t* src = base + (size_t)(ry0 - 2 + tid) * pitch + (size_t)rx0 * CT - (pre ? 16 : 0);
@@ -167,31 +138,30 @@ __global__ void __launch_bounds__(kFrThreads, 4) k_frontend_rows(const uint8_t* 
     // records of slice row h start at ((y0 W + x0 sh) + h sw + w) C   (32 bits: an image has < 2^32 samples)
     uint32_t out_idx = (((uint32_t)y0 * (uint32_t)g.W + (uint32_t)x0 * (uint32_t)sh) + ((uint32_t)h * (uint32_t)sw + (uint32_t)w)) * CT;
 
-    const int8_t* q11 = lut->q11 + kQB;
-    const int8_t* q5 = lut->q5 + kQB;
+    const int8_t* q11 = lut.q11 + kQB;
+    const int8_t* q5 = lut.q5 + kQB;
     const uint32_t* my_row = reinterpret_cast<const uint32_t*>(raw + ((16 - 2 * CT) & ~3) + PX * CT * tid);
 
     mbar_wait(bar, 0);
 
-    // planes of row y-1 for pixels x-1 .. x+PX (index j+1), and the row y-2 term of the hash for pixels x .. x+PX-1
-    Px<CT> top[PX + 2];
+    // Two plane arrays that swap roles every row (the loop is unrolled by two): pixels x-2 .. x+PX of the row in hand
+    // (index j+2) and of the row above; n5 carries the row y-2 term of the hash for pixels x .. x+PX-1.
+    Px<CT> pa[PX + 3], pb[PX + 3];
     int n5[PX][CT];
 #pragma unroll
-    for (int j = 0; j < PX + 2; ++j)
+    for (int j = 0; j < PX + 3; ++j)
 #pragma unroll
-        for (int c = 0; c < CT; ++c) top[j].v[c] = 0;
+        for (int c = 0; c < CT; ++c) pb[j].v[c] = 0;
 #pragma unroll
     for (int j = 0; j < PX; ++j)
 #pragma unroll
         for (int c = 0; c < CT; ++c) n5[j][c] = 0;
 
-#pragma unroll 1
-    for (int r = 0; r < kFrRows + 2; ++r) {
+    auto do_row = [&](int r, Px<CT> (&cur)[PX + 3], const Px<CT> (&top)[PX + 3]) {
         uint32_t wv[S::kWords];
         const uint32_t* rp = my_row + r * (S::kRowBytes / 4);
 #pragma unroll
         for (int k = 0; k < S::kWords; ++k) wv[k] = rp[k];
-        Px<CT> cur[PX + 3];                                                // pixels x-2 .. x+PX (index j+2)
 #pragma unroll
         for (int j = 0; j < PX + 3; ++j) cur[j] = planes_at<CT>(wv, S::kShift + j * CT);
 
@@ -205,8 +175,8 @@ __global__ void __launch_bounds__(kFrThreads, 4) k_frontend_rows(const uint8_t* 
                     for (int c = 0; c < CT; ++c) {
                         // the slice's first two and last columns: llcomp.hpp:417-422 with h > 1
                         int l = cur[j + 1].v[c], L = cur[j].v[c];
-                        const int t = top[j + 1].v[c];
-                        int tl = top[j].v[c], tr = top[j + 2].v[c];
+                        const int t = top[j + 2].v[c];
+                        int tl = top[j + 1].v[c], tr = top[j + 3].v[c];
                         if (j == 0) { l = wl ? t : l; tl = wl ? t : tl; }
                         if (j <= 1) L = wl ? l : L;
                         if (j == PX - 1) tr = wr ? t : tr;
@@ -218,12 +188,12 @@ __global__ void __launch_bounds__(kFrThreads, 4) k_frontend_rows(const uint8_t* 
 #pragma unroll
                     for (int c = 0; c < CT; ++c) {
                         const int wj = w + j;                               // llcomp.hpp:417-422
-                        const int top_c = top[j + 1].v[c];
+                        const int top_c = top[j + 2].v[c];
                         const int l = wj > 0 ? cur[j + 1].v[c] : (h > 0 ? top_c : 128);
                         const int t = h > 0 ? top_c : l;
                         const int L = wj > 1 ? cur[j].v[c] : l;
-                        const int tl = (h > 0 && wj > 0) ? top[j].v[c] : t;
-                        const int tr = (h > 0 && wj < sw - 1) ? top[j + 2].v[c] : t;
+                        const int tl = (h > 0 && wj > 0) ? top[j + 1].v[c] : t;
+                        const int tr = (h > 0 && wj < sw - 1) ? top[j + 3].v[c] : t;
                         // T = t on the first two rows of a slice: q5(0) = 0
                         rec[j * CT + c] = code_sample(cur[j + 2].v[c], l, L, tl, t, tr, 0, q11, q5);
                     }
@@ -242,47 +212,54 @@ __global__ void __launch_bounds__(kFrThreads, 4) k_frontend_rows(const uint8_t* 
                 out_idx = ((uint32_t)y0 * (uint32_t)g.W + (uint32_t)x0 * (uint32_t)sh + (uint32_t)w) * CT;
             }
         }
-        // this row becomes row y-1; its difference to the old row y-1 is the next row's T - t
+        // the difference of this row to the one above is the next row's T - t
 #pragma unroll
         for (int j = 0; j < PX; ++j)
 #pragma unroll
-            for (int c = 0; c < CT; ++c) n5[j][c] = 3025 * q5[top[j + 1].v[c] - cur[j + 2].v[c]];
-#pragma unroll
-        for (int j = 0; j < PX + 2; ++j) top[j] = cur[j + 1];
+            for (int c = 0; c < CT; ++c) n5[j][c] = 3025 * q5[top[j + 2].v[c] - cur[j + 2].v[c]];
+    };
+#pragma unroll 1
+    for (int r = 0; r < ROWS + 2; r += 2) {
+        do_row(r, pa, pb);
+        do_row(r + 1, pb, pa);
     }
 }
+
+// PX pixels per thread and ROWS rows per region: 3 channels -> 8 x 16 (a thread's row is 24 samples, 6 x 128-bit
+// stores; the region row is 1024 pixels), 4 channels -> 4 x 32.
+template <int CT> struct FrPick;
+template <> struct FrPick<3> { static constexpr int PX = LLC_FR_PX3, ROWS = LLC_FR_ROWS3, MINB = LLC_FR_MINB3; };
+template <> struct FrPick<4> { static constexpr int PX = 4, ROWS = 32, MINB = 3; };
 
 }  // namespace
 
 // true when the streaming kernel can take this geometry (the caller falls back to frontend.cu otherwise)
 bool frontend_rows_applicable(const uint8_t* d_pixels, const Geom& g) {
     if (g.C != 3 && g.C != 4) return false;
-    if (((size_t)g.W * g.C) % 16 != 0 || g.tw % 4 != 0 || g.W % 4 != 0) return false;
+    const int px = g.C == 3 ? FrPick<3>::PX : FrPick<4>::PX, rows = g.C == 3 ? FrPick<3>::ROWS : FrPick<4>::ROWS;
+    if (((size_t)g.W * g.C) % 16 != 0 || g.tw % px != 0 || g.W % px != 0) return false;
     if ((reinterpret_cast<uintptr_t>(d_pixels) & 15) != 0) return false;
     if (g.image_samples() >= (1ull << 32)) return false;                   // 32-bit record index inside an image
-    if ((g.H + kFrRows - 1) / kFrRows > 65535 || g.n_images > 65535) return false;
+    if ((g.H + rows - 1) / rows > 65535 || g.n_images > 65535) return false;
     return true;
 }
 
-cudaError_t configure_frontend_rows() {
-    cudaError_t e = cudaFuncSetAttribute(k_frontend_rows<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         FrShape<3, 4>::kSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_frontend_rows<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrShape<4, 4>::kSmem);
-    return e;
+template <int CT>
+static cudaError_t launch_rows(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st) {
+    using P = FrPick<CT>;
+    using S = FrShape<CT, P::PX, P::ROWS>;
+    static cudaError_t configured = cudaFuncSetAttribute(k_frontend_rows<CT, P::PX, P::ROWS, P::MINB>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem);
+    if (configured != cudaSuccess) return configured;
+    dim3 grid((g.W + S::kRegionW - 1) / S::kRegionW, (g.H + P::ROWS - 1) / P::ROWS, g.n_images);
+    k_frontend_rows<CT, P::PX, P::ROWS, P::MINB><<<grid, kFrThreads, S::kSmem, st>>>(d_pixels, g, d_sym);
+    return cudaGetLastError();
 }
 
+cudaError_t configure_frontend_rows() { return cudaSuccess; }   // the kernels configure themselves at first launch
+
 cudaError_t launch_frontend_rows(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st) {
-    if (g.C == 3) {
-        using S = FrShape<3, 4>;
-        dim3 grid((g.W + S::kRegionW - 1) / S::kRegionW, (g.H + kFrRows - 1) / kFrRows, g.n_images);
-        k_frontend_rows<3, 4><<<grid, kFrThreads, S::kSmem, st>>>(d_pixels, g, d_sym);
-    } else {
-        using S = FrShape<4, 4>;
-        dim3 grid((g.W + S::kRegionW - 1) / S::kRegionW, (g.H + kFrRows - 1) / kFrRows, g.n_images);
-        k_frontend_rows<4, 4><<<grid, kFrThreads, S::kSmem, st>>>(d_pixels, g, d_sym);
-    }
-    return cudaGetLastError();
+    return g.C == 3 ? launch_rows<3>(d_pixels, g, d_sym, st) : launch_rows<4>(d_pixels, g, d_sym, st);
 }
 
 }  // namespace llc

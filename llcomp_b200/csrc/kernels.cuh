@@ -14,7 +14,10 @@ struct Switches {
     bool coder_split = false;         // LLCOMP_CODER_SPLIT       model pass -> HBM queue -> range pass
     bool decoder_smem_state = false;  // LLCOMP_DECODER_SMEM_STATE
     bool model_smem_state = false;    // LLCOMP_MODEL_SMEM_STATE
+    bool coder_records = false;       // LLCOMP_CODER_RECORDS     fused coder always reads K1's record array
+    bool coder_pixels = false;        // LLCOMP_CODER_PIXELS      fused coder always computes its records from the pixels
     int fused_ns = 0;                 // LLCOMP_FUSED_NS          slices per coder CTA; 0 = automatic
+    int groups = 0;                   // LLCOMP_GROUPS            image groups of the pipelined host-buffer calls; 0 = automatic
 };
 const Switches& switches();
 void reload_switches();
@@ -41,8 +44,17 @@ cudaError_t launch_range_pass(const uint16_t* d_queue, const uint64_t* d_qoff, c
 // K2 fused: records -> per-slice scratch payloads in one kernel (model / chain / helper warp roles), no bin
 //     queue in HBM.  d_gstate != nullptr: the state rows live there (n_slices x 63,408 B, zeroed by the launch);
 //     nullptr: in shared memory.  fused_global_state_bytes() says which one a stand-alone launch should use.
-cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const Geom& g, uint8_t* d_scratch, uint32_t* d_slice_bytes,
-                                     int* d_status, uint8_t* d_gstate, cudaStream_t st);
+//     Exactly one of d_sym / d_pixels: with d_pixels (3- and 4-channel images, fused_coder_takes_pixels) the model
+//     warps compute the records from the pixels themselves and no record array exists.
+//     n_concurrent: slices of all fused-coder launches that run at the same time as this one (pipelined host-buffer
+//     encode), this launch included; 0 = this launch has the device to itself.  It sizes the CTAs (slices per CTA).
+cudaError_t launch_slice_coder_fused(const uint32_t* d_sym, const uint8_t* d_pixels, const Geom& g, uint8_t* d_scratch,
+                                     uint32_t* d_slice_bytes, int* d_status, uint8_t* d_gstate, cudaStream_t st,
+                                     uint64_t n_concurrent = 0);
+// can: the geometry allows it (3 or 4 channels, a solo arrangement).  takes: ... and it is what a call should do --
+// forced by a switch, or because the record array (4 bytes per sample) would not fit beside everything else.
+bool fused_coder_can_take_pixels(const Geom& g);
+bool fused_coder_takes_pixels(const Geom& g, bool record_array_fits = true);
 uint64_t fused_global_state_bytes(uint64_t n_slices);
 cudaError_t configure_slice_coder();
 

@@ -8,14 +8,16 @@
 // so llcompc.cpp:33 and llcompd.cpp:26 compile against it unchanged.  All arithmetic happens in
 // libllcomp_b200.so (CUDA, sm_100a); nothing here computes a single sample and there is no CPU fallback.
 //
-// New (the reference has no slicing / batching): Options{tile_w, tile_h, device} overloads and
-// compressBatch / decompressBatch.
+// New (the reference has no slicing / batching / devices): Options{tile_w, tile_h, device, devices} overloads and
+// compressBatch / decompressBatch.  Options::devices with two or more entries spreads a batch (image-wise) or one
+// tiled image (by bands of tile rows) over several GPUs of the box; the bytes do not depend on it.
 #pragma once
 #include <cstdint>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/llcomp_b200.h"
@@ -36,6 +38,7 @@ struct RawImage {                                            // llcomp.hpp:454-4
 struct Options {
     int tile_w = 0, tile_h = 0;   // 0 = one slice per image: byte-identical to the reference stream
     int device = 0;
+    std::vector<int> devices;     // >= 2 entries: shard over these GPUs (llcomp_b200_multi_*); else `device` alone
 };
 
 namespace detail {
@@ -56,6 +59,28 @@ inline llcomp_ctx* context(int device) {
     return ctxs[device].get();
 }
 
+struct MultiDeleter { void operator()(llcomp_multi* m) const { llcomp_b200_multi_destroy(m); } };
+
+inline llcomp_multi* multi_context(const std::vector<int>& devices) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::vector<int>, std::unique_ptr<llcomp_multi, MultiDeleter>>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& e : cache)
+        if (e.first == devices) return e.second.get();
+    llcomp_multi* m = nullptr;
+    if (llcomp_b200_multi_create(devices.data(), (int)devices.size(), &m) != LLCOMP_OK)
+        throw std::runtime_error("llcomp: no usable CUDA device (this build has no CPU path)");
+    cache.emplace_back(devices, std::unique_ptr<llcomp_multi, MultiDeleter>(m));
+    return m;
+}
+
+// RawImage carries 16-bit dimensions (llcomp.hpp:454-459); the reference truncates larger ones silently
+// (SURVEY.md defect D3), this refuses them.
+inline void check_u16(int w, int h) {
+    if (w > 0xFFFF || h > 0xFFFF)
+        throw std::length_error("llcomp: image dimensions above 65535 do not fit llcomp::RawImage; use the C ABI");
+}
+
 // The two reference exceptions keep their exact text (llcomp.hpp:233, :466) so callers that print
 // e.what() (llcompd.cpp:33) behave the same.
 [[noreturn]] inline void raise(llcomp_ctx* c, int status) {
@@ -69,6 +94,16 @@ inline std::vector<uint8_t> compressImage(const std::vector<uint8_t>& rgb, int w
                                           const Options& opt) {
     if (rgb.size() != (size_t)width * height * channels)     // assert at llcomp.hpp:361
         throw std::invalid_argument("llcomp: rgb.size() != width*height*channels");
+    if (opt.devices.size() >= 2) {                           // bands of tile rows over several GPUs
+        llcomp_multi* m = detail::multi_context(opt.devices);
+        llcomp_geometry g{width, height, channels, opt.tile_w, opt.tile_h, 1};
+        std::vector<uint8_t> out(llcomp_b200_stream_bound(&g));
+        uint64_t off[2] = {0, 0};
+        const int rc = llcomp_b200_multi_encode_batch(m, rgb.data(), &g, out.data(), out.size(), off);
+        if (rc != LLCOMP_OK) detail::raise(llcomp_b200_multi_ctx(m, 0), rc);
+        out.resize(off[1]);
+        return out;
+    }
     llcomp_ctx* c = detail::context(opt.device);
     uint8_t* s = nullptr;
     size_t n = 0;
@@ -84,7 +119,22 @@ inline std::vector<uint8_t> compressImage(const std::vector<uint8_t>& rgb, int w
 }
 
 inline RawImage decompressImage(const std::vector<uint8_t>& data, const Options& opt) {
-    llcomp_ctx* c = detail::context(opt.device);
+    llcomp_ctx* c = detail::context(opt.devices.size() >= 2 ? opt.devices[0] : opt.device);
+    {
+        int w = 0, h = 0, ch = 0, tw = 0, th = 0;
+        const int rc = llcomp_b200_peek(data.data(), data.size(), &w, &h, &ch, &tw, &th);
+        if (rc != LLCOMP_OK) detail::raise(c, rc);
+        detail::check_u16(w, h);
+        if (opt.devices.size() >= 2) {
+            llcomp_multi* m = detail::multi_context(opt.devices);
+            RawImage img{std::vector<uint8_t>((size_t)w * h * ch), (uint16_t)w, (uint16_t)h, (uint8_t)ch};
+            const uint64_t off[2] = {0, data.size()};
+            llcomp_geometry g{};
+            const int rc2 = llcomp_b200_multi_decode_batch(m, data.data(), off, 1, img.pixels.data(), img.pixels.size(), &g);
+            if (rc2 != LLCOMP_OK) detail::raise(llcomp_b200_multi_ctx(m, 0), rc2);
+            return img;
+        }
+    }
     uint8_t* px = nullptr;
     int w = 0, h = 0, ch = 0;
     const int rc = llcomp_b200_decode(c, data.data(), data.size(), &px, &w, &h, &ch);
@@ -101,11 +151,17 @@ inline std::vector<std::vector<uint8_t>> compressBatch(const std::vector<uint8_t
                                                        int height, int channels, const Options& opt = Options{}) {
     llcomp_geometry g{width, height, channels, opt.tile_w, opt.tile_h, n_images};
     if (pixels.size() != llcomp_b200_sample_count(&g)) throw std::invalid_argument("llcomp: batch size mismatch");
-    llcomp_ctx* c = detail::context(opt.device);
     std::vector<uint8_t> buf(llcomp_b200_stream_bound(&g));
     std::vector<uint64_t> off(n_images + 1);
-    const int rc = llcomp_b200_encode_batch(c, pixels.data(), &g, buf.data(), buf.size(), off.data());
-    if (rc != LLCOMP_OK) detail::raise(c, rc);
+    if (opt.devices.size() >= 2) {
+        llcomp_multi* m = detail::multi_context(opt.devices);
+        const int rc = llcomp_b200_multi_encode_batch(m, pixels.data(), &g, buf.data(), buf.size(), off.data());
+        if (rc != LLCOMP_OK) detail::raise(llcomp_b200_multi_ctx(m, 0), rc);
+    } else {
+        llcomp_ctx* c = detail::context(opt.device);
+        const int rc = llcomp_b200_encode_batch(c, pixels.data(), &g, buf.data(), buf.size(), off.data());
+        if (rc != LLCOMP_OK) detail::raise(c, rc);
+    }
     std::vector<std::vector<uint8_t>> out(n_images);
     for (int k = 0; k < n_images; ++k) out[k].assign(buf.begin() + off[k], buf.begin() + off[k + 1]);
     return out;
@@ -117,9 +173,10 @@ inline std::vector<RawImage> decompressBatch(const std::vector<std::vector<uint8
     std::vector<RawImage> out;
     if (streams.empty()) return out;
     int w = 0, h = 0, ch = 0, tw = 0, th = 0;
-    llcomp_ctx* c = detail::context(opt.device);
+    llcomp_ctx* c = detail::context(opt.devices.size() >= 2 ? opt.devices[0] : opt.device);
     int rc = llcomp_b200_peek(streams[0].data(), streams[0].size(), &w, &h, &ch, &tw, &th);
     if (rc != LLCOMP_OK) detail::raise(c, rc);
+    detail::check_u16(w, h);
     std::vector<uint8_t> cat;
     std::vector<uint64_t> off(streams.size() + 1, 0);
     for (size_t k = 0; k < streams.size(); ++k) off[k + 1] = off[k] + streams[k].size();
@@ -128,7 +185,11 @@ inline std::vector<RawImage> decompressBatch(const std::vector<std::vector<uint8
     const size_t per_image = (size_t)w * h * ch;
     std::vector<uint8_t> px(per_image * streams.size());
     llcomp_geometry g{};
-    rc = llcomp_b200_decode_batch(c, cat.data(), off.data(), (int)streams.size(), px.data(), px.size(), &g);
+    if (opt.devices.size() >= 2)
+        rc = llcomp_b200_multi_decode_batch(detail::multi_context(opt.devices), cat.data(), off.data(), (int)streams.size(),
+                                            px.data(), px.size(), &g);
+    else
+        rc = llcomp_b200_decode_batch(c, cat.data(), off.data(), (int)streams.size(), px.data(), px.size(), &g);
     if (rc != LLCOMP_OK) detail::raise(c, rc);
     out.reserve(streams.size());
     for (size_t k = 0; k < streams.size(); ++k)

@@ -1,7 +1,8 @@
 // llcompc -- encoder tool; same contract as /root/reference/llcompc.cpp: `llcompc <image>` writes
 // `<image>.llcomp`, exit 0 on success, 1 on a load/open failure.  Image loading is PNM/PAM instead of
 // stb_image (not vendored by the reference); the codec call is the reference's own line (llcompc.cpp:33).
-// Extra, optional: --tile WxH (sliced container), --device N, and more than one image: consecutive files of the
+// Extra, optional: --tile WxH (sliced container), --device N, --gpus N (shard a batch image-wise, or one tiled image by
+// bands of tile rows, over GPUs 0..N-1; the bytes do not change), and more than one image: consecutive files of the
 // same size are coded in ONE batch call (one slice per image is one serial chain on the GPU, so a batch is
 // where the throughput comes from); every `<image>.llcomp` is the same bytes as a single-file run writes.
 #include <cstdio>
@@ -33,12 +34,24 @@ int main(int argc, char** argv) {
             if (std::sscanf(argv[++i], "%dx%d", &opt.tile_w, &opt.tile_h) != 2) { std::cerr << "--tile wants WxH\n"; return 1; }
         } else if (!std::strcmp(argv[i], "--device") && i + 1 < argc) {
             opt.device = std::atoi(argv[++i]);
+        } else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) {
+            const int n = std::atoi(argv[++i]);
+            if (n < 1) { std::cerr << "--gpus wants a positive count\n"; return 1; }
+            opt.devices.clear();
+            for (int d = 0; d < n && n > 1; ++d) opt.devices.push_back(d);
+        } else if (!std::strcmp(argv[i], "--devices") && i + 1 < argc) {        // explicit list, e.g. 0,0 or 2,3
+            opt.devices.clear();
+            for (const char* p = argv[++i]; *p;) {
+                opt.devices.push_back(std::atoi(p));
+                while (*p && *p != ',') ++p;
+                if (*p == ',') ++p;
+            }
         } else {
             files.push_back(argv[i]);
         }
     }
     if (files.empty()) {
-        std::cerr << "Usage: " << argv[0] << " <image_path> [more images ...] [--tile WxH] [--device N]" << std::endl;
+        std::cerr << "Usage: " << argv[0] << " <image_path> [more images ...] [--tile WxH] [--device N] [--gpus N]" << std::endl;
         return 1;
     }
     std::vector<pnm::Image> imgs(files.size());

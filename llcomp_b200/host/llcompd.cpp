@@ -2,8 +2,10 @@
 // decoded image next to it, exit 1 on open/decompress errors (message "Error decompressing image: <what>",
 // llcompd.cpp:33), 2 on unknown exceptions.  Output is PNM/PAM (`<file>.ppm|.pgm|.pam`) instead of PNG:
 // stb_image_write is not vendored by the reference.  Extra: more than one file; consecutive files with the same
-// header (same size and tile grid) are decoded in one batch call.
+// header (same size and tile grid) are decoded in one batch call; --device N / --gpus N as in llcompc.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <iterator>
@@ -20,11 +22,30 @@ static void write_image(const std::string& stream_path, const llcomp::RawImage& 
 }
 
 int main(int argc, char** argv) {
-    if (argc < 2) {
-        std::cerr << "Usage: " << argv[0] << " <image_path> [more files ...]" << std::endl;
+    llcomp::Options opt;
+    std::vector<std::string> files;
+    for (int i = 1; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "--device") && i + 1 < argc) {
+            opt.device = std::atoi(argv[++i]);
+        } else if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) {
+            const int n = std::atoi(argv[++i]);
+            opt.devices.clear();
+            for (int d = 0; d < n && n > 1; ++d) opt.devices.push_back(d);
+        } else if (!std::strcmp(argv[i], "--devices") && i + 1 < argc) {
+            opt.devices.clear();
+            for (const char* p = argv[++i]; *p;) {
+                opt.devices.push_back(std::atoi(p));
+                while (*p && *p != ',') ++p;
+                if (*p == ',') ++p;
+            }
+        } else {
+            files.push_back(argv[i]);
+        }
+    }
+    if (files.empty()) {
+        std::cerr << "Usage: " << argv[0] << " <image_path> [more files ...] [--device N] [--gpus N]" << std::endl;
         return 1;
     }
-    std::vector<std::string> files(argv + 1, argv + argc);
     std::vector<std::vector<uint8_t>> streams(files.size());
     for (size_t k = 0; k < files.size(); ++k) {
         std::ifstream inFile(files[k], std::ios::binary);
@@ -36,7 +57,7 @@ int main(int argc, char** argv) {
     }
     try {
         if (files.size() == 1) {
-            auto [pixels, width, height, channels] = llcomp::decompressImage(streams[0]);   // llcompd.cpp:26
+            auto [pixels, width, height, channels] = llcomp::decompressImage(streams[0], opt);   // llcompd.cpp:26
             write_image(files[0], llcomp::RawImage{std::move(pixels), width, height, channels});
             return 0;
         }
@@ -51,10 +72,10 @@ int main(int argc, char** argv) {
             size_t e = k + 1;
             while (e < files.size() && same_geometry(streams[k], streams[e])) ++e;
             if (e - k == 1) {
-                write_image(files[k], llcomp::decompressImage(streams[k]));
+                write_image(files[k], llcomp::decompressImage(streams[k], opt));
             } else {
                 const std::vector<std::vector<uint8_t>> group(streams.begin() + k, streams.begin() + e);
-                const auto imgs = llcomp::decompressBatch(group);
+                const auto imgs = llcomp::decompressBatch(group, opt);
                 for (size_t i = k; i < e; ++i) write_image(files[i], imgs[i - k]);
             }
             k = e;

@@ -91,3 +91,59 @@ def test_many_files_are_coded_as_batches(tools, tmp_path):
     assert subprocess.run([llcompd] + [s + ".llcomp" for s in srcs[:3]]).returncode == 0
     for src, img in zip(srcs[:3], imgs[:3]):
         assert (read_pnm_payload(src + ".llcomp.ppm", img.size) == img.reshape(-1)).all(), src
+
+
+def test_gpus_option_shards_without_changing_bytes(tools, tmp_path):
+    """--devices 0,0 (two shards; works on a one-GPU box) and --gpus N: a batch goes image-wise, a tiled image by
+    bands of tile rows; every output file is the same bytes as without the option."""
+    llcompc, llcompd = tools
+    imgs = [oracle.generate(96, 64, 3, 4, 40 + k) for k in range(5)]
+    srcs = []
+    for k, img in enumerate(imgs):
+        srcs.append(str(tmp_path / ("g%d.ppm" % k)))
+        write_pnm(srcs[-1], img)
+    assert subprocess.run([llcompc] + srcs + ["--devices", "0,0"]).returncode == 0
+    for src, img in zip(srcs, imgs):
+        with open(src + ".llcomp", "rb") as f:
+            assert f.read() == oracle.compress(img), src
+    assert subprocess.run([llcompd] + [s + ".llcomp" for s in srcs] + ["--devices", "0,0"]).returncode == 0
+    for src, img in zip(srcs, imgs):
+        assert (read_pnm_payload(src + ".llcomp.ppm", img.size) == img.reshape(-1)).all(), src
+    big = oracle.generate(320, 256, 3, 4, 3)
+    src = str(tmp_path / "big.ppm")
+    write_pnm(src, big)
+    assert subprocess.run([llcompc, src, "--tile", "64x64"]).returncode == 0
+    with open(src + ".llcomp", "rb") as f:
+        want = f.read()
+    assert subprocess.run([llcompc, src, "--tile", "64x64", "--devices", "0,0,0"]).returncode == 0
+    with open(src + ".llcomp", "rb") as f:
+        assert f.read() == want
+    assert subprocess.run([llcompd, src + ".llcomp", "--devices", "0,0,0"]).returncode == 0
+    assert (read_pnm_payload(src + ".llcomp.ppm", big.size) == big.reshape(-1)).all()
+    import torch
+    if torch.cuda.device_count() >= 2:
+        assert subprocess.run([llcompc, src, "--tile", "64x64", "--gpus", "2"]).returncode == 0
+        with open(src + ".llcomp", "rb") as f:
+            assert f.read() == want
+
+
+def test_unmodified_reference_tools_run_on_the_gpu_library(tmp_path):
+    """llcomp_b200/host/_ref_cli/ holds the reference's own llcompc.cpp / llcompd.cpp, compiled UNCHANGED against
+    llcomp_b200/host/llcomp.hpp (make -C llcomp_b200/host ref_cli; stb replaced by the PNM stubs of tests/stubs).
+    They must behave like the reference tools: same stream bytes, exact pixels back."""
+    c_tool, d_tool = (os.path.join(HOST, "_ref_cli", n) for n in ("llcompc", "llcompd"))
+    if not (os.path.exists(c_tool) and os.path.exists(d_tool)):
+        pytest.skip("reference CLIs were not built (no /root/reference at build time)")
+    img = oracle.generate(160, 100, 3, 4, 2024)
+    src = str(tmp_path / "r.ppm")
+    write_pnm(src, img)
+    assert subprocess.run([c_tool, src]).returncode == 0
+    with open(src + ".llcomp", "rb") as f:
+        assert f.read() == oracle.compress(img)
+    assert subprocess.run([d_tool, src + ".llcomp"]).returncode == 0
+    assert (read_pnm_payload(src + ".llcomp.png", img.size) == img.reshape(-1)).all()    # the stub writes PNM bytes
+    bad = str(tmp_path / "bad.llcomp")
+    with open(bad, "wb") as f:
+        f.write(bytes([0x77, 3, 1, 0, 1, 0, 0]))
+    r = subprocess.run([d_tool, bad], capture_output=True, text=True)
+    assert r.returncode == 1 and "Invalid magic number" in r.stderr

@@ -314,8 +314,9 @@ def test_many_slices_decode_with_state_behind_l1(codec):
 
 
 def test_fused_coder_variants_agree(codec):
-    """The fused coder serves 3..7 slices per CTA with one CTA per SM (the default picks by slice count; 13..17 force
-    it), or 1, 2, 4 slices per chain warp in the round-1 arrangement (LLCOMP_FUSED_NS), always with the state rows
+    """The fused coder serves 1..7 slices per CTA with one CTA per SM (the default picks by slice count; 11..17 force
+    it, 23..27 give the recurrence warp a sub-partition of its own), or 1, 2, 4 slices per chain warp in the round-1
+    arrangement (LLCOMP_FUSED_NS), always with the state rows
     behind L1, or one slice per CTA with the rows in shared memory (LLCOMP_MODEL_SMEM_STATE): same bytes from all of
     them, with ragged slices and a slice count (378) that leaves the last CTA of every form partly empty."""
     import torch
@@ -327,12 +328,15 @@ def test_fused_coder_variants_agree(codec):
     codec.finish()
     n = int(offsets[-1])
     for var, val in (("LLCOMP_FUSED_NS", "1"), ("LLCOMP_FUSED_NS", "2"), ("LLCOMP_FUSED_NS", "4"),
+                     ("LLCOMP_FUSED_NS", "11"), ("LLCOMP_FUSED_NS", "12"), ("LLCOMP_FUSED_NS", "13"),
                      ("LLCOMP_FUSED_NS", "14"), ("LLCOMP_FUSED_NS", "15"), ("LLCOMP_FUSED_NS", "16"),
-                     ("LLCOMP_FUSED_NS", "17"), ("LLCOMP_MODEL_SMEM_STATE", "1")):
-        with switched(codec, **{var: val}):
-            p2, o2 = codec.encode_device(d_px, g)
-            codec.finish()
-        assert torch.equal(o2, offsets) and torch.equal(p2[:n], payload[:n]), (var, val)
+                     ("LLCOMP_FUSED_NS", "17"), ("LLCOMP_FUSED_NS", "23"), ("LLCOMP_FUSED_NS", "24"),
+                     ("LLCOMP_FUSED_NS", "25"), ("LLCOMP_FUSED_NS", "27"), ("LLCOMP_MODEL_SMEM_STATE", "1")):
+        for pixels in (0, 1):                                        # records from K1's record array / from the pixels
+            with switched(codec, **{var: val, "LLCOMP_CODER_PIXELS": pixels}):
+                p2, o2 = codec.encode_device(d_px, g)
+                codec.finish()
+            assert torch.equal(o2, offsets) and torch.equal(p2[:n], payload[:n]), (var, val, pixels)
     off = offsets.cpu().numpy()
     tiles = tiles_of(200, 180, 32, 32)
     for img, t in ((0, 0), (3, 6), (8, 41), (5, 20)):                 # corners and an interior slice against the oracle
@@ -378,8 +382,11 @@ def test_alternate_kernels_agree(codec):
     codec.finish()
     n = int(offsets[-1])
     assert torch.equal(out.view(imgs.shape), d_px)
-    for switch in ("LLCOMP_FRONTEND_SIMPLE", "LLCOMP_FRONTEND_TILED", "LLCOMP_DECODER_SIMPLE", "LLCOMP_CODER_SPLIT"):
-        with switched(codec, **{switch: 1}):
+    # (LLCOMP_CODER_PIXELS: the fused coder computes its records from the pixels itself, no K1 and no record array)
+    for env in ({"LLCOMP_CODER_PIXELS": 1}, {"LLCOMP_FRONTEND_SIMPLE": 1}, {"LLCOMP_FRONTEND_TILED": 1},
+                {"LLCOMP_DECODER_SIMPLE": 1}, {"LLCOMP_CODER_SPLIT": 1}):
+        switch = "+".join(env)
+        with switched(codec, **env):
             p2, o2 = codec.encode_device(d_px, g)
             out2 = codec.decode_device(p2, o2, g)
             codec.finish()
@@ -460,3 +467,32 @@ def test_wide_tile_uses_global_row_scratch(codec):
     s = codec.compress(img, 20000, 6, 3)
     assert s == oracle.compress(img)
     assert (codec.decompress(s).pixels == img).all()
+
+
+def test_coder_works_from_pixels_when_the_record_array_does_not_fit(codec):
+    """no 4-byte-per-sample intermediate.  By default K1 writes a record array for the coder
+    (faster); when the array exceeds its budget the coder's model warps compute the records from the pixels inside
+    the CTA.  Same bytes either way; RGB and RGBA; whole-image slices and ragged tiles; host-buffer path too."""
+    import torch
+    for c, tw, th in ((3, 0, 0), (4, 48, 40), (3, 100, 7)):
+        imgs = np.stack([oracle.generate(136, 90, c, 6, 600 + k) for k in range(5)])
+        g = codec.geometry(136, 90, c, tw, th, 5)
+        d_px = torch.from_numpy(imgs).cuda()
+        want_p, want_o = codec.encode_device(d_px, g)
+        codec.finish()
+        assert not codec.last_encode_from_pixels()
+        n = int(want_o[-1])
+        codec.set_record_budget(1000)                         # far less than 4 bytes x 183,600 samples
+        try:
+            got_p, got_o = codec.encode_device(d_px, g)
+            codec.finish()
+            assert codec.last_encode_from_pixels()
+            buf, off = codec.compress_batch(imgs, tw, th)
+            assert codec.last_encode_from_pixels()
+        finally:
+            codec.set_record_budget(60 << 30)
+        assert torch.equal(got_o, want_o) and torch.equal(got_p[:n], want_p[:n]), (c, tw, th)
+        buf2, off2 = codec.compress_batch(imgs, tw, th)
+        assert (off == off2).all() and (buf[: int(off[-1])] == buf2[: int(off[-1])]).all()
+        if tw == 0:
+            assert buf[: int(off[1])].tobytes() == oracle.compress(imgs[0])
