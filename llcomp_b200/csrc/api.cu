@@ -134,6 +134,7 @@ bool make_geom(const llcomp_geometry* in, Geom* g) {
     g->tiles_x = (g->W + g->tw - 1) / g->tw;
     g->tiles_y = (g->H + g->th - 1) / g->th;
     if ((uint64_t)g->tw * g->th * g->C >= (1ull << 30)) return false;   // per-slice byte counts are u32
+    if ((uint64_t)g->tiles_x * (uint64_t)g->tiles_y >= (1ull << 31)) return false;   // slices_per_image() is u32
     if (g->n_slices() >= (1ull << 31)) return false;
     return true;
 }

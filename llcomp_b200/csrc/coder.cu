@@ -1111,7 +1111,7 @@ __global__ void __launch_bounds__(32 * fused_warps(NS, kSolo)) k_slice_coder_fus
     }
 }
 
-static int sm_count() {
+static int sm_count() {                                      // of the current device (the devices of a box are alike)
     static const int n = [] {
         int dev = 0, v = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1)
@@ -1137,8 +1137,7 @@ template <int NS, bool kGlobalState, int kSolo, bool kPixels>
 static cudaError_t launch_fused_from(const uint32_t* d_sym, const uint8_t* d_pixels, const Geom& g, uint8_t* d_scratch,
                                      uint32_t* d_slice_bytes, int* d_status, uint2* gs, unsigned n, cudaStream_t st) {
     constexpr int kSmem = fused_smem_bytes(NS, kGlobalState, kPixels);
-    static cudaError_t configured = cudaFuncSetAttribute(k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    const cudaError_t configured = ensure_dynamic_smem<k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels>>(kSmem);
     if (configured != cudaSuccess) return configured;
     k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels><<<(n + NS - 1) / NS, 32 * fused_warps(NS, kSolo), kSmem, st>>>(
         d_sym, d_pixels, g, d_scratch, d_slice_bytes, d_status, gs, n);

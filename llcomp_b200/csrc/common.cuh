@@ -2,7 +2,7 @@
 //
 // Format constants follow /root/reference/llcomp.hpp:17-32; the adaptive bit model follows
 // llcomp.hpp:250-294 (nextStateMps / nextStateLps / stateProbability).  The tables are generated
-// from their pair structure and checked entry-by-entry against the oracle in tests/test_tables.py
+// from their pair structure and checked entry-by-entry against the oracle in tests/test_abi.py (test_model_tables_equal_oracle)
 // (through llcomp_b200_debug_table).
 #pragma once
 #include <cstdint>

@@ -248,8 +248,7 @@ template <int CT>
 static cudaError_t launch_rows(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st) {
     using P = FrPick<CT>;
     using S = FrShape<CT, P::PX, P::ROWS>;
-    static cudaError_t configured = cudaFuncSetAttribute(k_frontend_rows<CT, P::PX, P::ROWS, P::MINB>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmem);
+    const cudaError_t configured = ensure_dynamic_smem<k_frontend_rows<CT, P::PX, P::ROWS, P::MINB>>(S::kSmem);
     if (configured != cudaSuccess) return configured;
     dim3 grid((g.W + S::kRegionW - 1) / S::kRegionW, (g.H + P::ROWS - 1) / P::ROWS, g.n_images);
     k_frontend_rows<CT, P::PX, P::ROWS, P::MINB><<<grid, kFrThreads, S::kSmem, st>>>(d_pixels, g, d_sym);

@@ -2,7 +2,24 @@
 #pragma once
 #include "common.cuh"
 
+#include <atomic>
+
 namespace llc {
+
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per device (the attribute is per device, and the
+// multi-device entry points launch the same kernel on several of them from several host threads).
+template <auto kernel>                                       // the kernel itself, not its type: kernels of one signature must not share the flag
+inline cudaError_t ensure_dynamic_smem(int bytes) {
+    static std::atomic<unsigned long long> done{0};         // one static per kernel: bit d = device d
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 // Test switches (DESIGN.md "Test switches"): each selects the plain variant of one stage so that tests can check the
 // default kernels against it; none selects a CPU path.  Read from the environment (LLCOMP_*) when a context is
