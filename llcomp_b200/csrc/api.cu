@@ -30,12 +30,14 @@ void reload_switches() {
     s.frontend_simple = on("LLCOMP_FRONTEND_SIMPLE");
     s.frontend_tiled = on("LLCOMP_FRONTEND_TILED");
     s.decoder_simple = on("LLCOMP_DECODER_SIMPLE");
+    s.decoder_v1 = on("LLCOMP_DECODER_V1");
     s.coder_split = on("LLCOMP_CODER_SPLIT");
     s.decoder_smem_state = on("LLCOMP_DECODER_SMEM_STATE");
     s.model_smem_state = on("LLCOMP_MODEL_SMEM_STATE");
     s.coder_records = on("LLCOMP_CODER_RECORDS");
     s.coder_pixels = on("LLCOMP_CODER_PIXELS");
     if (const char* v = getenv("LLCOMP_FUSED_NS")) s.fused_ns = atoi(v);
+    if (const char* v = getenv("LLCOMP_DECODER_VARIANT")) s.decoder_variant = atoi(v);
     if (const char* v = getenv("LLCOMP_GROUPS")) s.groups = std::max(0, std::min(atoi(v), (int)llcomp_ctx_groups));
     g_switches = s;
 }

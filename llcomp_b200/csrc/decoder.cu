@@ -398,14 +398,23 @@ __global__ void __launch_bounds__(32) k_slice_decoder_fast(const uint8_t* __rest
 }
 
 static int fast_line_bytes(const Geom& g) { return 2 * (((min(g.tw, g.W) * g.C + 7) & ~7) * 2); }
+// shared memory of one slice with the state rows in it: the chain (default) or the round-1 fast kernel
+static int fast_smem_with_state(const Geom& g) {
+    return switches().decoder_v1 ? kFastBase + fast_line_bytes(g) : chain_decoder_smem_bytes(g, false);
+}
+constexpr int kChainMaxSmem = 226 * 1024;                   // a CTA can have 227 KB on sm_100, static shared memory included
 static bool fast_decoder_fits(const Geom& g) {
-    return g.C >= 1 && g.C <= 4 && kFastBase + fast_line_bytes(g) <= 200 * 1024;
+    if (g.C < 1 || g.C > 4) return false;
+    if (switches().decoder_v1) return fast_smem_with_state(g) <= 200 * 1024;
+    return chain_decoder_smem_bytes(g, true) <= kChainMaxSmem;          // the rows can always go behind L1
 }
 // State in shared memory while every slice of the call finds a shared-memory slot at once (3 per SM for
 // <= 1024-wide RGB tiles), else state in global memory behind L1 (7+ slices per SM, one wave).
 static bool decoder_wants_global_state(const Geom& g, bool shared_launch) {
-    const int per_sm = (228 * 1024) / (kFastBase + fast_line_bytes(g) + 1024);
-    if (!fast_decoder_fits(g) || switches().decoder_smem_state) return false;
+    const int per_sm = (228 * 1024) / (fast_smem_with_state(g) + 1024);
+    if (!fast_decoder_fits(g)) return false;
+    if (!switches().decoder_v1 && fast_smem_with_state(g) > kChainMaxSmem) return true;   // wide tiles: no room for the rows
+    if (switches().decoder_smem_state) return false;
     // a launch that runs beside other launches of the same call (pipelined host-buffer decode) must not take
     // shared-memory slots away from them
     return shared_launch || g.n_slices() > (uint64_t)per_sm * 148;
@@ -442,6 +451,15 @@ cudaError_t launch_slice_decoder(const uint8_t* d_payload, const uint64_t* d_off
                                  cudaStream_t st, bool shared_launch) {
     const uint64_t ns = g.n_slices();
     if (ns == 0 || ns > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    if (fast_decoder_fits(g) && !switches().decoder_simple && !switches().decoder_v1) {
+        uint8_t* gs = nullptr;
+        if (decoder_wants_global_state(g, shared_launch)) {
+            gs = d_gstate;
+            const cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);   // all states start at 0
+            if (e != cudaSuccess) return e;
+        }
+        return launch_slice_decoder_chain(d_payload, d_offsets, g, d_pixels, gs, d_status, st);
+    }
     if (fast_decoder_fits(g) && !switches().decoder_simple) {
         const unsigned n = (unsigned)ns;
         if (decoder_wants_global_state(g, shared_launch)) {

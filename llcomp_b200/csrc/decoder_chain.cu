@@ -1,0 +1,87 @@
+// decoder_chain.cu -- K5, default form for 1..4 channels: one warp per slice, lane 0 runs the chain of
+// decoder_chain.cuh (see there for the design), the whole warp stages the payload, prepares the row-above part of the
+// context hashes before a row and does the inverse colour transform and the pixel stores after it.
+// /root/reference/llcomp.hpp:475-545.
+#include "common.cuh"
+#include "decoder_chain.cuh"
+#include "kernels.cuh"
+
+namespace llc {
+
+__constant__ ModelTables c_tables_chain = make_tables();
+
+// kGlobalState: the slice's state rows live in global memory (pre-zeroed by the host) behind L1, else in shared memory
+// after the chain's own buffers.
+template <int CT, bool kGlobalState, int kV>
+__global__ void __launch_bounds__(32) k_slice_decoder_chain(const uint8_t* __restrict__ payload,
+                                                            const uint64_t* __restrict__ offsets, Geom g,
+                                                            uint8_t* __restrict__ pixels, int* __restrict__ status,
+                                                            uint2* __restrict__ gstate) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x;
+    const uint64_t s = blockIdx.x;
+    const Slice sl = slice_of(g, s);
+    // The window address of the shared memory goes through a volatile shared-memory word: a value the compiler has
+    // loaded cannot be rematerialised (it otherwise re-reads SR_CgaCtaId and rebuilds the base inside the sample loop,
+    // in front of every table request).
+    __shared__ uint32_t s_base;
+    if (lane == 0) s_base = (uint32_t)__cvta_generic_to_shared(smem);
+    __syncwarp();
+    const uint32_t base = *reinterpret_cast<volatile uint32_t*>(&s_base);
+    const int row_elems = min(g.tw, g.W) * CT;                            // one layout for every slice of the launch
+    const dchain::Layout L = dchain::make_layout(row_elems, base + (kGlobalState ? 0u : (uint32_t)kStateBytes));
+    dchain::Smem m;
+    dchain::StateMem<kGlobalState> st;
+    st.g = reinterpret_cast<uint64_t>(gstate + (size_t)s * kContexts);
+    st.s = base;                                                          // rows first (16-byte aligned), then the chain's buffers
+    if (!kGlobalState) {
+        uint4* rows = reinterpret_cast<uint4*>(smem);
+        for (int i = lane; i < kStateBytes / 16; i += 32) rows[i] = make_uint4(0, 0, 0, 0);
+    }
+    const size_t pitch = (size_t)g.W * CT;
+    uint8_t* dst = pixels + (size_t)sl.img * g.H * pitch + (size_t)sl.y0 * pitch + (size_t)sl.x0 * CT;
+    const uint8_t* src = payload + offsets[s];
+    const uint32_t len = (uint32_t)(offsets[s + 1] - offsets[s]);
+    const bool ok = dchain::decode_slice_rows<CT, kGlobalState, kV>(m, L, st, c_tables_chain.entry, src, len, sl.w, sl.h, dst,
+                                                                 pitch, lane, 32, [] { __syncwarp(); });
+    if (!ok && lane == 0) atomicCAS(status, kDevOk, kDevBadExponent);
+}
+
+int chain_decoder_smem_bytes(const Geom& g, bool global_state) {
+    return (int)dchain::layout_bytes(std::min(g.tw, g.W) * g.C) + (global_state ? 0 : kStateBytes);
+}
+
+template <int CT, bool kGlobalState, int kV = 0>
+static cudaError_t launch_chain(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g, uint8_t* d_pixels,
+                                int* d_status, uint2* gs, unsigned n, cudaStream_t st) {
+    const int smem = chain_decoder_smem_bytes(g, kGlobalState);
+    const cudaError_t configured = ensure_dynamic_smem<k_slice_decoder_chain<CT, kGlobalState, kV>>(226 * 1024);
+    if (configured != cudaSuccess) return configured;
+    k_slice_decoder_chain<CT, kGlobalState, kV><<<n, 32, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, gs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_slice_decoder_chain(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
+                                       uint8_t* d_pixels, uint8_t* d_gstate, int* d_status, cudaStream_t st) {
+    const unsigned n = (unsigned)g.n_slices();
+    uint2* gs = reinterpret_cast<uint2*>(d_gstate);
+    // measurement variants (LLCOMP_DECODER_VARIANT=1..3, three channels, rows behind L1): see Chain's kV
+    if (switches().decoder_variant && g.C == 3 && d_gstate) {
+        switch (switches().decoder_variant) {
+            case 1: return launch_chain<3, true, 1>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st);
+            case 2: return launch_chain<3, true, 2>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st);
+            case 3: return launch_chain<3, true, 3>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st);
+        }
+    }
+#define LLC_CASE(CT)                                                                                                    \
+    case CT:                                                                                                            \
+        return d_gstate ? launch_chain<CT, true>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st)              \
+                        : launch_chain<CT, false>(d_payload, d_offsets, g, d_pixels, d_status, nullptr, n, st);
+    switch (g.C) {
+        LLC_CASE(1) LLC_CASE(2) LLC_CASE(3) LLC_CASE(4)
+    }
+#undef LLC_CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace llc

@@ -28,11 +28,13 @@ struct Switches {
     bool frontend_simple = false;     // LLCOMP_FRONTEND_SIMPLE   one thread per pixel
     bool frontend_tiled = false;      // LLCOMP_FRONTEND_TILED    round-1 tiled front end instead of the streaming one
     bool decoder_simple = false;      // LLCOMP_DECODER_SIMPLE    plain chain, three row buffers
+    bool decoder_v1 = false;          // LLCOMP_DECODER_V1        round-1 fast decoder (k_slice_decoder_fast) instead of the chain of decoder_chain.cuh
     bool coder_split = false;         // LLCOMP_CODER_SPLIT       model pass -> HBM queue -> range pass
     bool decoder_smem_state = false;  // LLCOMP_DECODER_SMEM_STATE
     bool model_smem_state = false;    // LLCOMP_MODEL_SMEM_STATE
     bool coder_records = false;       // LLCOMP_CODER_RECORDS     fused coder always reads K1's record array
     bool coder_pixels = false;        // LLCOMP_CODER_PIXELS      fused coder always computes its records from the pixels
+    int decoder_variant = 0;          // LLCOMP_DECODER_VARIANT   measurement variants of the chain decoder (decoder_chain.cu)
     int fused_ns = 0;                 // LLCOMP_FUSED_NS          slices per coder CTA; 0 = automatic
     int groups = 0;                   // LLCOMP_GROUPS            image groups of the pipelined host-buffer calls; 0 = automatic
 };
@@ -92,5 +94,9 @@ uint64_t decoder_global_state_bytes(const Geom& g, bool shared_launch = false);
 cudaError_t configure_slice_decoder();
 // bytes of global line scratch the decoder needs for this geometry (0 when the rows fit in shared memory)
 uint64_t decoder_line_scratch_bytes(const Geom& g);
+// K5, default form for 1..4 channels (decoder_chain.cu): d_gstate != nullptr -> state rows there (zeroed by the caller)
+cudaError_t launch_slice_decoder_chain(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
+                                       uint8_t* d_pixels, uint8_t* d_gstate, int* d_status, cudaStream_t st);
+int chain_decoder_smem_bytes(const Geom& g, bool global_state);
 
 }  // namespace llc

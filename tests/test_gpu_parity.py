@@ -384,7 +384,8 @@ def test_alternate_kernels_agree(codec):
     assert torch.equal(out.view(imgs.shape), d_px)
     # (LLCOMP_CODER_PIXELS: the fused coder computes its records from the pixels itself, no K1 and no record array)
     for env in ({"LLCOMP_CODER_PIXELS": 1}, {"LLCOMP_FRONTEND_SIMPLE": 1}, {"LLCOMP_FRONTEND_TILED": 1},
-                {"LLCOMP_DECODER_SIMPLE": 1}, {"LLCOMP_CODER_SPLIT": 1}):
+                {"LLCOMP_DECODER_SIMPLE": 1}, {"LLCOMP_DECODER_V1": 1}, {"LLCOMP_DECODER_V1": 1, "LLCOMP_DECODER_SMEM_STATE": 1},
+                {"LLCOMP_DECODER_SMEM_STATE": 1}, {"LLCOMP_CODER_SPLIT": 1}):
         switch = "+".join(env)
         with switched(codec, **env):
             p2, o2 = codec.encode_device(d_px, g)
@@ -392,6 +393,28 @@ def test_alternate_kernels_agree(codec):
             codec.finish()
         assert torch.equal(o2, offsets) and torch.equal(p2[:n], payload[:n]), switch
         assert torch.equal(out2, out), switch
+
+
+def test_decoder_forms_agree_on_many_slices(codec):
+    """The chain decoder (default; decoder_chain.cuh) with its state rows behind L1 (many slices) and in shared memory,
+    its measurement variants, the round-1 fast decoder and the plain chain: the same pixels from all of them, and the
+    pixels are the originals.  1, 2, 3 and 4 channels; noise from flat to uniform random bytes."""
+    import torch
+    for c, noise, w, h, tw, th, n in ((3, 4, 320, 96, 64, 32, 40), (1, -1, 256, 64, 32, 32, 64), (4, 16, 128, 64, 32, 16, 40),
+                                      (2, 0, 96, 64, 48, 16, 80), (3, 64, 1024, 8, 1024, 8, 4)):
+        imgs = np.stack([oracle.generate(w, h, c, noise, 4000 + k) for k in range(n)])
+        g = codec.geometry(w, h, c, tw, th, n)
+        d_px = torch.from_numpy(imgs).cuda()
+        payload, offsets = codec.encode_device(d_px, g)
+        out = codec.decode_device(payload, offsets, g)
+        codec.finish()
+        assert torch.equal(out.view(imgs.shape), d_px), (c, noise)
+        for env in ({"LLCOMP_DECODER_SMEM_STATE": 1}, {"LLCOMP_DECODER_V1": 1}, {"LLCOMP_DECODER_SIMPLE": 1},
+                    {"LLCOMP_DECODER_VARIANT": 1}, {"LLCOMP_DECODER_VARIANT": 2}, {"LLCOMP_DECODER_VARIANT": 3}):
+            with switched(codec, **env):
+                out2 = codec.decode_device(payload, offsets, g)
+                codec.finish()
+            assert torch.equal(out2, out), (c, noise, env)
 
 
 def test_batch_of_megapixel_images_matches_reference(codec):
