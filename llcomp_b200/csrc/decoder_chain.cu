@@ -65,12 +65,12 @@ cudaError_t launch_slice_decoder_chain(const uint8_t* d_payload, const uint64_t*
                                        uint8_t* d_pixels, uint8_t* d_gstate, int* d_status, cudaStream_t st) {
     const unsigned n = (unsigned)g.n_slices();
     uint2* gs = reinterpret_cast<uint2*>(d_gstate);
-    // measurement variants (LLCOMP_DECODER_VARIANT=1..3, three channels, rows behind L1): see Chain's kV
+    // measurement variants (LLCOMP_DECODER_VARIANT=1, 2, 4, three channels, rows behind L1): see Chain's kV
     if (switches().decoder_variant && g.C == 3 && d_gstate) {
         switch (switches().decoder_variant) {
             case 1: return launch_chain<3, true, 1>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st);
             case 2: return launch_chain<3, true, 2>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st);
-            case 3: return launch_chain<3, true, 3>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st);
+            case 4: return launch_chain<3, true, 4>(d_payload, d_offsets, g, d_pixels, d_status, gs, n, st);
         }
     }
 #define LLC_CASE(CT)                                                                                                    \

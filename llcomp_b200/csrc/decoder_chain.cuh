@@ -138,6 +138,17 @@ inline uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel) {          // __byte
 }
 #endif
 
+#if defined(__CUDACC__)
+#define LLC_UNLIKELY(x) __builtin_expect(!!(x), 0)
+// range * q + 255, pinned where it is written (the compiler would otherwise sink it below the renormalisation test)
+__device__ __forceinline__ uint32_t mad255(uint32_t r, uint32_t q) {
+    uint32_t t; asm volatile("mad.lo.u32 %0, %1, %2, 255;" : "=r"(t) : "r"(r), "r"(q)); return t;
+}
+#else
+#define LLC_UNLIKELY(x) (x)
+inline uint32_t mad255(uint32_t r, uint32_t q) { return r * q + 255u; }
+#endif
+
 LLC_HD int iabs(int v) { return v < 0 ? -v : v; }
 LLC_HD int imin(int a, int b) { return a < b ? a : b; }
 LLC_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -237,8 +248,8 @@ Renormed renorm_out(uint32_t R, uint32_t cS, uint32_t pos, uint32_t nextb, uint3
     return r;
 }
 
-// kV: variant bits for measurements (0 = default).  1: renormalisation out of line; 2: part 2 of the context left to
-// the assembler's own placement.
+// kV: variant bits for measurements.  1: renormalisation out of line; 2: part 2 of the context left to the assembler's
+// own placement; 4: products taken ahead of the renormalisation test (residual_spec).
 template <int CT, bool kGlobal, int kV = 0>
 struct Chain {
     Smem m;
@@ -395,7 +406,7 @@ struct Chain {
                         for (;;) {
                             const Ent e4 = ent_of(row.y, 0);
                             if (!bin_flat<0>(e4, row.y)) break;
-                            if (++e > 31) { bad = true; return 0; }
+                            if (++e > 31) { bad = true; pos = 0x80000000u; break; }   // ends the pixel loop at its next check
                         }
                         uint32_t value = 2u + bin_flat<1>(e5, row.y);
                         for (int k = e - 2; k >= 0; --k) {
@@ -411,8 +422,97 @@ struct Chain {
         return diff;
     }
 
+    // ---- the decisions, second form (kV & 4): the product of the decision that FOLLOWS is taken as soon as the range is
+    // known, before it is known whether the range has to be renormalised first.  One decision in ten renormalises: a
+    // cold loop does it and takes the product again.  Written in line and predicated by the assembler, the test, the
+    // shift and the product sit between every two decisions with their full fixed latencies, taken or not.
+#define LLC_PREP(TQ, Q)                                            \
+    uint32_t TQ = mad255(R, (Q));                                  \
+    while (LLC_UNLIKELY(R < 0x100u)) { renorm(); TQ = mad255(R, (Q)); }
+#define LLC_SETTLE() while (LLC_UNLIKELY(R < 0x100u)) renorm();
+#define LLC_SBIN(TQ, E, W, S0, S1, ARM1, ARM0)                     \
+    {                                                              \
+        const uint32_t r0_ = (TQ) >> 8;                            \
+        if (cS >= (TQ)) {                                          \
+            cS -= (TQ) & ~0xFFu;                                   \
+            R -= r0_;                                              \
+            W = bperm(W, (E).nx, S1);                              \
+            ARM1                                                   \
+        } else {                                                   \
+            R = r0_;                                               \
+            W = bperm(W, (E).nx, S0);                              \
+            ARM0                                                   \
+        }                                                          \
+    }
+    // branch-free decision whose product tq is already taken; leaves the range settled
+    template <int kB>
+    LLC_HD uint32_t flat_s(uint32_t tq, const Ent e, uint32_t& w) {
+        const uint32_t r0 = tq >> 8, t0 = tq & ~0xFFu;
+        const bool bit = cS >= tq;
+        R = bit ? R - r0 : r0;
+        cS = bit ? cS - t0 : cS;
+        constexpr uint32_t s0 = kB == 0 ? 0x3214u : kB == 1 ? 0x3240u : kB == 2 ? 0x3410u : 0x4210u;
+        constexpr uint32_t s1 = kB == 0 ? 0x3215u : kB == 1 ? 0x3250u : kB == 2 ? 0x3510u : 0x5210u;
+        w = bperm(w, e.nx, bit ? s1 : s0);
+        return bit ? 1u : 0u;
+    }
+    // mantissa and sign for an exponent E <= 2 reached with the range not yet settled
+    template <int E>
+    LLC_HD int mantissa_sign_s(Row& row, const Ent e5, const Ent e6, const Ent e7) {
+        uint32_t value = 1;
+        if (E >= 1) {
+            LLC_PREP(t5, e5.q)
+            value = 2u + flat_s<1>(t5, e5, row.y);
+        }
+        if (E >= 2) {
+            LLC_PREP(t6, e6.q)
+            value += value + flat_s<2>(t6, e6, row.y);
+        }
+        LLC_PREP(t7, e7.q)
+        const uint32_t sgn = flat_s<3>(t7, e7, row.y);
+        LLC_SETTLE()
+        return sgn ? -(int)value : (int)value;
+    }
+    LLC_HD int residual_spec(Row& row, const Ent e0, const Ent e1, const Ent e2, const Ent e3, const Ent e5, const Ent e6,
+                             const Ent e7) {
+        int diff = 0;
+        const uint32_t t0q = mad255(R, e0.q);                            // the range is settled between samples
+        LLC_SBIN(t0q, e0, row.x, 0x3214u, 0x3215u, { LLC_SETTLE() diff = 0; }, {
+            LLC_PREP(t1q, e1.q)
+            LLC_SBIN(t1q, e1, row.x, 0x3240u, 0x3250u, {
+                LLC_PREP(t2q, e2.q)
+                LLC_SBIN(t2q, e2, row.x, 0x3410u, 0x3510u, {
+                    LLC_PREP(t3q, e3.q)
+                    LLC_SBIN(t3q, e3, row.x, 0x4210u, 0x5210u, {
+                        // exponent >= 3: context 4 repeats (llcomp.hpp:230-235), then the general mantissa loop
+                        LLC_SETTLE()
+                        int e = 3;
+                        for (;;) {
+                            const Ent e4 = ent_of(row.y, 0);
+                            if (!bin_flat<0>(e4, row.y)) break;
+                            if (++e > 31) { bad = true; pos = 0x80000000u; break; }   // ends the pixel loop at its next check
+                        }
+                        uint32_t value = 2u + bin_flat<1>(e5, row.y);
+                        for (int k = e - 2; k >= 0; --k) {
+                            const Ent e6d = ent_of(row.y, 2);
+                            value += value + bin_flat<2>(e6d, row.y);
+                        }
+                        const uint32_t sgn = bin_flat<3>(e7, row.y);
+                        diff = sgn ? -(int)value : (int)value;
+                    }, { diff = mantissa_sign_s<2>(row, e5, e6, e7); })
+                }, { diff = mantissa_sign_s<1>(row, e5, e6, e7); })
+            }, { diff = mantissa_sign_s<0>(row, e5, e6, e7); })
+        })
+        return diff;
+    }
+#undef LLC_PREP
+#undef LLC_SETTLE
+#undef LLC_SBIN
+
     // Pixels [w0, w_end) of the row in hand; stops early (returns the pixel reached) when the payload staged in the
-    // ring could run out (pos > pos_limit), or on a bad stream.
+    // ring could run out (pos > pos_limit).  A bad stream (exponent > 31) sets `bad` and a huge `pos`: the loop then
+    // stops at the next pixel (what it decodes until then is discarded by the caller), so the sample loop does not
+    // carry a test of the flag.
     template <bool kFirstRow>
     LLC_HD int run(int w0, int w_end, uint32_t pos_limit) {
         int w = w0;
@@ -440,8 +540,8 @@ struct Chain {
                 if (CT > 1) part2((i + CT - 1) % CT, (kV & 2) ? 0u : e0.q >> 9);
                 // ---- [C] the decisions
                 const int pr = pred[i], left = l[i];
-                int diff = residual_with(row, e0, e1, e2, e3, e5, e6, e7);
-                if (bad) return w;
+                int diff = (kV & 4) ? residual_spec(row, e0, e1, e2, e3, e5, e6, e7)
+                                    : residual_with(row, e0, e1, e2, e3, e5, e6, e7);
                 // ---- [D] write back, reconstruct, part 1 of the plane's next sample
                 st.store((uint32_t)ah, row);
                 whash[i] = ah; wrow[i] = row;

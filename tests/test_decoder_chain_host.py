@@ -25,13 +25,18 @@ def chain():
         subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-I/usr/local/cuda/include",
                         "-o", so, src], check=True)
     lib = C.CDLL(so)
-    lib.chain_decode_tile.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    lib.chain_decode_tile_v.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
 
     def dec(payload: bytes, w: int, h: int, c: int):
+        """Both forms of the decision code (Chain's kV 0 and 4) must agree; returns what they return."""
         buf = np.frombuffer(payload, dtype=np.uint8).copy() if len(payload) else np.zeros(1, np.uint8)
-        out_px = np.zeros((h, w, c), np.uint8)
-        rc = lib.chain_decode_tile(buf.ctypes.data, len(payload), w, h, c, out_px.ctypes.data, w * c)
-        return rc, out_px
+        res = []
+        for variant in (0, 4):
+            out_px = np.zeros((h, w, c), np.uint8)
+            rc = lib.chain_decode_tile_v(buf.ctypes.data, len(payload), w, h, c, out_px.ctypes.data, w * c, variant)
+            res.append((rc, out_px))
+        assert res[0][0] == res[1][0] and (res[0][1] == res[1][1]).all(), "the two forms of the chain disagree"
+        return res[0]
     return dec
 
 
@@ -66,3 +71,20 @@ def test_chain_follows_the_oracle_on_damaged_streams(chain, w, h, c, noise):
         assert rc == wrc
         if want is not None:
             assert (out == want).all()
+
+
+def test_chain_reports_a_runaway_exponent(chain):
+    """A nonzero flag followed by all ones: the exponent runs past 31 -> "Invalid exponent" (llcomp.hpp:232-233); the
+    chain flags it and stops at the next pixel.  Same payload as tests/test_gpu_parity.py::test_error_behaviour."""
+    bad = bytes([2, 250]) + b"\xff" * 60
+    hits = 0
+    for c, w, h in ((1, 4, 4), (1, 9, 2), (2, 4, 4), (3, 8, 5), (4, 3, 3)):
+        try:
+            oracle.decode_tile(bad, w, h, c)
+            want = 0
+        except oracle.OracleError as e:
+            assert e.code == 2
+            want, hits = 2, hits + 1
+        rc, _ = chain(bad, w, h, c)
+        assert rc == want, (c, w, h)
+    assert hits >= 1
