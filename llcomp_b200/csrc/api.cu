@@ -38,6 +38,7 @@ void reload_switches() {
     s.coder_pixels = on("LLCOMP_CODER_PIXELS");
     if (const char* v = getenv("LLCOMP_FUSED_NS")) s.fused_ns = atoi(v);
     if (const char* v = getenv("LLCOMP_DECODER_VARIANT")) s.decoder_variant = atoi(v);
+    if (const char* v = getenv("LLCOMP_FRONTEND_VARIANT")) s.frontend_variant = atoi(v);
     if (const char* v = getenv("LLCOMP_GROUPS")) s.groups = std::max(0, std::min(atoi(v), (int)llcomp_ctx_groups));
     g_switches = s;
 }

@@ -356,7 +356,7 @@ struct Chain {
         const uint32_t tq_ = R * (E).q + 255u;                     \
         const uint32_t r0_ = tq_ >> 8;                             \
         if (cS >= tq_) {                                           \
-            cS -= tq_ & ~0xFFu;                                    \
+            cS -= r0_ << 8;                                        \
             R -= r0_;                                              \
             W = bperm(W, (E).nx, S1);                              \
             if (R < 0x100u) renorm();                              \
@@ -518,7 +518,7 @@ struct Chain {
         int w = w0;
         for (; w < w_end; ++w) {
             if (pos > pos_limit) break;
-            const uint32_t j2 = 2u * (uint32_t)(w * CT);
+            const uint32_t aA = bufA + 2u * (uint32_t)(w * CT), aB = bufB + 2u * (uint32_t)(w * CT);   // pixel w in the row buffers
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -534,8 +534,8 @@ struct Chain {
                 }
                 const Ent e0 = ent_of(row.x, 0), e1 = ent_of(row.x, 1), e2 = ent_of(row.x, 2), e3 = ent_of(row.x, 3);
                 const Ent e5 = ent_of(row.y, 1), e6 = ent_of(row.y, 2), e7 = ent_of(row.y, 3);
-                const int t_next = kFirstRow ? 0 : m.s16(bufA + j2 + 2u * (CT + i));
-                const int p_next = m.s16(bufB + j2 + 2u * (CT + i));
+                const int t_next = kFirstRow ? 0 : m.s16(aA + 2u * (CT + i));
+                const int p_next = m.s16(aB + 2u * (CT + i));
                 // ---- [B] part 2 of the plane before this one (its quantiser look-ups have arrived)
                 if (CT > 1) part2((i + CT - 1) % CT, (kV & 2) ? 0u : e0.q >> 9);
                 // ---- [C] the decisions
@@ -546,7 +546,7 @@ struct Chain {
                 st.store((uint32_t)ah, row);
                 whash[i] = ah; wrow[i] = row;
                 const int cur = (int)(int16_t)(pr + (hsh < 0 ? -diff : diff));   // llcomp.hpp:526-529
-                m.st16(bufB + j2 + 2u * i, cur);
+                m.st16(aB + 2u * i, cur);
                 part1<kFirstRow>(i, cur, w == 0 ? cur : left, t_next, p_next);   // w == 0: the next sample's L = l (:496)
             }
         }

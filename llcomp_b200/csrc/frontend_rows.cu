@@ -87,7 +87,18 @@ struct FrShape {
     static_assert(ROWS % 2 == 0, "the row loop is unrolled by two");
 };
 
-template <int CT, int PX, int ROWS, int MINB>
+// kV, variants kept for cross-checks and measurements (0 = default).
+// bit 0 = the warp lays its row of records out in shared memory and the TMA unit stores it (UBLKCP.G.S), instead of
+// every thread storing its own 96 contiguous bytes with 128-bit stores.  A streaming kernel with this 1-read-4-write mix
+// and per-thread-contiguous stores tops out at 4.1 TB/s against 6.0 TB/s with whole-sector stores
+// (profiles/microbench/write_mix.cu), which is where this kernel sits -- but it sits there for another reason: with
+// TMA stores it takes 4.32 ms against 4.20, and with the staged row read back by the lanes for coalesced 128-bit stores
+// 4.63: its issue slots and its ALU pipe are 77 % busy with 12 warps per SM, it is bound by instructions per sample.
+// bit 2 = the round-2a sample code (five look-ups per sample, code_sample)
+// instead of the shared look-ups below.
+// (Measured and dropped: raw bytes fetched one by one instead of words + extraction, 4.49 against 4.17 ms; the colour
+// transform's division through a byte table, 4.24 ms.)
+template <int CT, int PX, int ROWS, int MINB, int kV>
 __global__ void __launch_bounds__(kFrThreads, MINB) k_frontend_rows(const uint8_t* __restrict__ pixels, Geom g,
                                                                     uint32_t* __restrict__ sym) {
     using S = FrShape<CT, PX, ROWS>;
@@ -95,6 +106,8 @@ __global__ void __launch_bounds__(kFrThreads, MINB) k_frontend_rows(const uint8_
     // static, so that a look-up is one LDS whose table address is an immediate: the difference that indexes it then
     // comes straight from the multiply-add pipe instead of a three-input add on the (busier) ALU pipe
     __shared__ __align__(16) QuantBytes lut;
+    constexpr int NV = PX * CT / 4;                                        // 16-byte words of records per thread and row
+    __shared__ __align__(128) uint4 stage[(kV & 1) ? kFrThreads * NV : 1];   // per warp: its row of records as it lies in HBM
     __shared__ __align__(8) unsigned long long bar_word;
     const uint32_t bar = smem_u32(&bar_word);
 
@@ -166,9 +179,40 @@ __global__ void __launch_bounds__(kFrThreads, MINB) k_frontend_rows(const uint8_
         for (int j = 0; j < PX + 3; ++j) cur[j] = planes_at<CT>(wv, S::kShift + j * CT);
 
         const int y = ry0 + r - 2;
-        if (r >= 2 && y < g.H && active) {
+        const int h_row = h;                                                // slice row of this image row (h moves on below)
+        if (r >= 2 && y < g.H) {                                            // warp-uniform
             uint32_t rec[PX * CT];
-            if (h >= 2) {
+            if (!active) {
+#pragma unroll
+                for (int k = 0; k < PX * CT; ++k) rec[k] = 0;
+            } else if (h >= 2 && !(kV & 4)) {
+                // Interior rows, shared look-ups.  With a3[j] = q11(t - tr) of sample j: q11(t - tl) of sample j is
+                // -a3[j-1] (the same two values of the row above, swapped); with v[j] = q11(top - cur) at column j:
+                // q11(l - tl) of sample j is -v[j-1], and 3025 q5 of the same difference is the next row's T - t term.
+                // Four look-ups and four subtractions per sample instead of five and five.
+#pragma unroll
+                for (int c = 0; c < CT; ++c) {
+                    int a3_prev = wl ? 0 : (int)q11[top[1].v[c] - top[2].v[c]];          // sample -1's t - tr; left edge: tl = t
+                    int v_prev = wl ? 0 : (int)q11[top[1].v[c] - cur[1].v[c]];          // column -1;        left edge: l = tl = t
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) {
+                        const int t = top[j + 2].v[c], x = cur[j + 2].v[c];
+                        int l = cur[j + 1].v[c], L = cur[j].v[c], tl = top[j + 1].v[c];
+                        if (j == 0) { l = wl ? t : l; tl = wl ? t : tl; }
+                        if (j <= 1) L = wl ? l : L;
+                        const int a3 = (j == PX - 1 && wr) ? 0 : (int)q11[t - top[j + 3].v[c]];   // right edge: tr = t
+                        const int vd = t - x;
+                        const int v = q11[vd];
+                        const int hash = (a3 * 11 + a3_prev) * 11 - v_prev + 605 * q5[L - l] + n5[j][c];   // :424-429
+                        n5[j][c] = 3025 * q5[vd];                                                          // next row's T - t
+                        a3_prev = a3;
+                        v_prev = v;
+                        const int hi = max(l, t), lo = min(l, t);
+                        const int pred = max(min(l + t - tl, hi), lo);                                    // median, :430
+                        rec[j * CT + c] = record_of(hash, x - pred);                                       // :431-436
+                    }
+                }
+            } else if (h >= 2) {
 #pragma unroll
                 for (int j = 0; j < PX; ++j)
 #pragma unroll
@@ -198,31 +242,59 @@ __global__ void __launch_bounds__(kFrThreads, MINB) k_frontend_rows(const uint8_
                         rec[j * CT + c] = code_sample(cur[j + 2].v[c], l, L, tl, t, tr, 0, q11, q5);
                     }
             }
-            uint4* out = reinterpret_cast<uint4*>(img_out + out_idx);
+            if (!(kV & 1)) {
+                if (active) {
+                    uint4* out = reinterpret_cast<uint4*>(img_out + out_idx);
 #pragma unroll
-            for (int k = 0; k < PX * CT / 4; ++k)
-                out[k] = make_uint4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-            // next row of the slice, or the first row of the tile row below
-            ++h;
-            out_idx += (uint32_t)sw * CT;
-            if (h == sh) {
-                y0 += g.th;
-                sh = min(g.th, g.H - y0);
-                h = 0;
-                out_idx = ((uint32_t)y0 * (uint32_t)g.W + (uint32_t)x0 * (uint32_t)sh + (uint32_t)w) * CT;
+                    for (int k = 0; k < NV; ++k)
+                        out[k] = make_uint4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+                }
+            } else {
+                // (variant) The warp lays its row of records out in shared memory as it lies in HBM and the TMA unit
+                // stores it: one bulk copy per run of lanes inside one slice (the whole warp, 3 KB, when the slice is at
+                // least 256 pixels wide), issued by the run's first lane.  Warp-level synchronisation only; the previous
+                // row's copy has long read its source when the wait is reached.
+                const int lane = tid & 31;
+                uint4* const st = stage + (tid >> 5) * 32 * NV + lane * NV;
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < NV; ++k) st[k] = make_uint4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (active && (lane == 0 || wl)) {
+                    const int run = min(32 - lane, (sw - w) / PX);            // lanes of this slice from here on
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(img_out + out_idx),
+                                 "r"(smem_u32(st)), "r"((uint32_t)run * NV * 16u) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (active) {
+                // next row of the slice, or the first row of the tile row below
+                ++h;
+                out_idx += (uint32_t)sw * CT;
+                if (h == sh) {
+                    y0 += g.th;
+                    sh = min(g.th, g.H - y0);
+                    h = 0;
+                    out_idx = ((uint32_t)y0 * (uint32_t)g.W + (uint32_t)x0 * (uint32_t)sh + (uint32_t)w) * CT;
+                }
             }
         }
-        // the difference of this row to the one above is the next row's T - t
+        // the difference of this row to the one above is the next row's T - t (the shared-look-up form has set it already)
+        if (!(r >= 2 && y < g.H && active && h_row >= 2 && !(kV & 4))) {
 #pragma unroll
-        for (int j = 0; j < PX; ++j)
+            for (int j = 0; j < PX; ++j)
 #pragma unroll
-            for (int c = 0; c < CT; ++c) n5[j][c] = 3025 * q5[top[j + 2].v[c] - cur[j + 2].v[c]];
+                for (int c = 0; c < CT; ++c) n5[j][c] = 3025 * q5[top[j + 2].v[c] - cur[j + 2].v[c]];
+        }
     };
 #pragma unroll 1
     for (int r = 0; r < ROWS + 2; r += 2) {
         do_row(r, pa, pb);
         do_row(r + 1, pb, pa);
     }
+    if (kV & 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the CTA's shared memory outlives its bulk stores
 }
 
 // PX pixels per thread and ROWS rows per region: 3 channels -> 8 x 16 (a thread's row is 24 samples, 6 x 128-bit
@@ -244,21 +316,33 @@ bool frontend_rows_applicable(const uint8_t* d_pixels, const Geom& g) {
     return true;
 }
 
-template <int CT>
+template <int CT, int kV = 0>
 static cudaError_t launch_rows(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st) {
     using P = FrPick<CT>;
     using S = FrShape<CT, P::PX, P::ROWS>;
-    const cudaError_t configured = ensure_dynamic_smem<k_frontend_rows<CT, P::PX, P::ROWS, P::MINB>>(S::kSmem);
+    const cudaError_t configured = ensure_dynamic_smem<k_frontend_rows<CT, P::PX, P::ROWS, P::MINB, kV>>(S::kSmem);
     if (configured != cudaSuccess) return configured;
     dim3 grid((g.W + S::kRegionW - 1) / S::kRegionW, (g.H + P::ROWS - 1) / P::ROWS, g.n_images);
-    k_frontend_rows<CT, P::PX, P::ROWS, P::MINB><<<grid, kFrThreads, S::kSmem, st>>>(d_pixels, g, d_sym);
+    k_frontend_rows<CT, P::PX, P::ROWS, P::MINB, kV><<<grid, kFrThreads, S::kSmem, st>>>(d_pixels, g, d_sym);
     return cudaGetLastError();
 }
 
 cudaError_t configure_frontend_rows() { return cudaSuccess; }   // the kernels configure themselves at first launch
 
 cudaError_t launch_frontend_rows(const uint8_t* d_pixels, const Geom& g, uint32_t* d_sym, cudaStream_t st) {
-    return g.C == 3 ? launch_rows<3>(d_pixels, g, d_sym, st) : launch_rows<4>(d_pixels, g, d_sym, st);
+    if (g.C == 3) {
+        switch (switches().frontend_variant) {                 // LLCOMP_FRONTEND_VARIANT: measurement variants (kV)
+            case 1: return launch_rows<3, 1>(d_pixels, g, d_sym, st);
+            case 4: return launch_rows<3, 4>(d_pixels, g, d_sym, st);
+            case 5: return launch_rows<3, 5>(d_pixels, g, d_sym, st);
+            default: return launch_rows<3, 0>(d_pixels, g, d_sym, st);
+        }
+    }
+    switch (switches().frontend_variant) {
+        case 1: return launch_rows<4, 1>(d_pixels, g, d_sym, st);
+        case 4: return launch_rows<4, 4>(d_pixels, g, d_sym, st);
+        default: return launch_rows<4, 0>(d_pixels, g, d_sym, st);
+    }
 }
 
 }  // namespace llc

@@ -384,6 +384,8 @@ def test_alternate_kernels_agree(codec):
     assert torch.equal(out.view(imgs.shape), d_px)
     # (LLCOMP_CODER_PIXELS: the fused coder computes its records from the pixels itself, no K1 and no record array)
     for env in ({"LLCOMP_CODER_PIXELS": 1}, {"LLCOMP_FRONTEND_SIMPLE": 1}, {"LLCOMP_FRONTEND_TILED": 1},
+                {"LLCOMP_FRONTEND_VARIANT": 1}, {"LLCOMP_FRONTEND_VARIANT": 5},
+                {"LLCOMP_FRONTEND_VARIANT": 4},
                 {"LLCOMP_DECODER_SIMPLE": 1}, {"LLCOMP_DECODER_V1": 1}, {"LLCOMP_DECODER_V1": 1, "LLCOMP_DECODER_SMEM_STATE": 1},
                 {"LLCOMP_DECODER_SMEM_STATE": 1}, {"LLCOMP_CODER_SPLIT": 1}):
         switch = "+".join(env)
