@@ -242,6 +242,11 @@ def main():
               "channels": C, "noise": args.noise, "tile": [tile_w or W, tile_h or H], "slices_per_gpu": None,
               "sharding": f"dp{world}", "l2": "inputs (>= 400 MB per GPU and step) are larger than the 126 MB L2"}
 
+    # slices a rank codes (pure arithmetic, so that both arms print the same config)
+    tiles_x = -(-W // tile_w) if tile_w else 1
+    tiles_y = -(-H // tile_h) if tile_h else 1
+    config["slices_per_gpu"] = per_rank * tiles_x * tiles_y
+
     # ------------------------------------------------------------------ reference arm (CPU only)
     if args.impl == "reference":
         if rank != 0:
@@ -287,7 +292,7 @@ def main():
     g = codec.geometry(W, H, C, tile_w, tile_h, n_img)
     n_slices = codec.slice_count(g)
     spi = n_slices // n_img
-    config["slices_per_gpu"] = n_slices
+    assert spi == tiles_x * tiles_y, "slice arithmetic of the bench and of the library disagree"
     raw = n_img * W * H * C                                  # this rank's raw bytes
     raw_job = total_images * W * H * C
     px = synth_batch(torch, n_img, W, H, C, args.noise, 1234, dev, first=first)
