@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(32 * fused_warps(NS, kSolo)) k_slice_coder_fus
         // record of this lane's sample in step k (32 samples per step; a step never straddles two chunks)
         auto step_record = [&](uint64_t k) -> uint32_t {
             const uint64_t first = k * 32u;
-            if (!kPixels) return first + lane < n ? in[first + lane] : 0u;
+            if (!kPixels) return first + lane < n ? __ldcs(in + first + lane) : 0u;   // read once: streaming, the state rows keep L2
             if (first >= n) return 0u;
             const uint32_t chunk = (uint32_t)(k / (uint32_t)C), sub = (uint32_t)(k - (uint64_t)chunk * C);
             while (rec_seen <= chunk) produce(rec_seen++);    // (a chunk two back is in registers by now: ring of four)

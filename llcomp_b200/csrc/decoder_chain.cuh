@@ -149,6 +149,16 @@ __device__ __forceinline__ uint32_t mad255(uint32_t r, uint32_t q) {
 inline uint32_t mad255(uint32_t r, uint32_t q) { return r * q + 255u; }
 #endif
 
+// Payload bytes and pixels pass once: streaming accesses (evict-first), so that they do not push the slices' state rows
+// -- 65 MB for 1024 slices, re-read all the time -- out of L2.
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t load_stream_u8(const uint8_t* p) { return __ldcs(p); }
+__device__ __forceinline__ void store_stream_u8(uint8_t* p, uint32_t v) { __stcs(p, (uint8_t)v); }
+#else
+inline uint32_t load_stream_u8(const uint8_t* p) { return *p; }
+inline void store_stream_u8(uint8_t* p, uint32_t v) { *p = (uint8_t)v; }
+#endif
+
 LLC_HD int iabs(int v) { return v < 0 ? -v : v; }
 LLC_HD int imin(int a, int b) { return a < b ? a : b; }
 LLC_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -185,7 +195,7 @@ LLC_HD void fill_tables(const Smem& m, const Layout& L, const uint32_t* entry, i
 LLC_HD uint32_t ring_refill(const Smem& m, const Layout& L, const uint8_t* src, uint32_t len, uint32_t filled,
                             uint32_t pos, int lane, int nl) {
     const uint32_t want = pos + kRingBytes;
-    for (uint32_t k = filled + lane; k < want; k += nl) m.st8(L.ring | (k & (kRingBytes - 1)), k < len ? src[k] : 0u);
+    for (uint32_t k = filled + lane; k < want; k += nl) m.st8(L.ring | (k & (kRingBytes - 1)), k < len ? load_stream_u8(src + k) : 0u);
     return want;
 }
 
@@ -219,12 +229,12 @@ LLC_HD void row_output(const Smem& m, uint32_t bufB, int w, uint8_t* dst, int la
             g -= (r + b) / 4;
             r += g;
             b += g;
-            dst[x * CT + 0] = (uint8_t)imax(0, imin(255, r));
-            dst[x * CT + 1] = (uint8_t)imax(0, imin(255, g));
-            dst[x * CT + 2] = (uint8_t)imax(0, imin(255, b));
-            if (CT == 4) dst[x * CT + 3] = (uint8_t)m.s16(a + 6);
+            store_stream_u8(dst + x * CT + 0, (uint32_t)imax(0, imin(255, r)));
+            store_stream_u8(dst + x * CT + 1, (uint32_t)imax(0, imin(255, g)));
+            store_stream_u8(dst + x * CT + 2, (uint32_t)imax(0, imin(255, b)));
+            if (CT == 4) store_stream_u8(dst + x * CT + 3, (uint32_t)m.s16(a + 6));
         } else {
-            for (int i = 0; i < CT; ++i) dst[x * CT + i] = (uint8_t)m.s16(a + 2 * i);
+            for (int i = 0; i < CT; ++i) store_stream_u8(dst + x * CT + i, (uint32_t)m.s16(a + 2 * i));
         }
     }
 }

@@ -419,6 +419,17 @@ def test_decoder_forms_agree_on_many_slices(codec):
             assert torch.equal(out2, out), (c, noise, env)
 
 
+def test_very_wide_slices_decode(codec):
+    """Slices 16384 samples-times-3 wide: the chain decoder's two row buffers take 197 KB of shared memory (state rows
+    behind L1); four channels at that width do not fit and take the plain chain.  Streams equal the oracle's, pixels
+    come back exactly."""
+    for c in (3, 4, 1):
+        img = oracle.generate(16384, 5, c, 6, 600 + c)
+        s = codec.compress(img, 16384, 5, c)
+        assert s == oracle.compress(img), c
+        assert (codec.decompress(s).pixels == img).all(), c
+
+
 def test_batch_of_megapixel_images_matches_reference(codec):
     """BASELINE configs[3] in small: 1024x1024 RGB images, one slice each, streams byte-identical to the oracle."""
     imgs = np.stack([oracle.generate(1024, 1024, 3, 4, 1234 + k) for k in range(3)])
