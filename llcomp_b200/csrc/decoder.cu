@@ -458,7 +458,7 @@ cudaError_t launch_slice_decoder(const uint8_t* d_payload, const uint64_t* d_off
             const cudaError_t e = cudaMemsetAsync(d_gstate, 0, ns * (uint64_t)kStateBytes, st);   // all states start at 0
             if (e != cudaSuccess) return e;
         }
-        return launch_slice_decoder_chain(d_payload, d_offsets, g, d_pixels, gs, d_status, st);
+        return launch_slice_decoder_chain(d_payload, d_offsets, g, d_pixels, gs, d_status, st, shared_launch);
     }
     if (fast_decoder_fits(g) && !switches().decoder_simple) {
         const unsigned n = (unsigned)ns;

@@ -34,39 +34,44 @@ namespace llc {
 namespace dchain {
 
 constexpr int kQC = 64;                          // quantiser tables cover [-64, 63]; q11 saturates at 35, q5 at 4
-constexpr int kRingBytes = 2048;                 // payload bytes staged ahead of the chain
+constexpr int kRingBytes = 1024;                 // payload bytes staged ahead of the chain
 constexpr int kMaxBytesPerSample = 66;           // a decision consumes at most one byte; <= 2*31+3 decisions + slack
 
 struct alignas(8) Ent { uint32_t q, nx; };       // q = 256 - P(bit = 1); nx = next state if 0 | next state if 1 << 8
 struct alignas(8) Row { uint32_t x, y; };        // the 8 sub-states of one context, one byte each
 
 // Layout of the chain's shared memory: 32-bit addresses (device: shared-window addresses; host: offsets into an arena).
-// The entry table and the payload ring start on multiples of 2048, so that `index | table` is the address of an element
-// (one three-input logic instruction instead of a mask and an add).
+// The tables are shared by the warps of a CTA (one slice per warp); every warp has its own payload ring and row buffers.
+// The entry table and the rings start on multiples of 1024, so that `index | table` is the address of an element (one
+// three-input logic instruction instead of a mask and an add).  Seven slices of 1024 RGB pixels take 94 KB: an SM that
+// decodes them as one CTA keeps 128 KB of L1 for their state rows (as seven CTAs with their own tables: 96 KB; the
+// chain's speed follows the rows' L1 hit rate).
 struct Layout {
-    uint32_t ent, q11, q5, ring, bufA, bufB, end;
+    uint32_t ent, q11, q5, ring, bufA, bufB, end;            // ring, bufA, bufB: this warp's; end: of the whole CTA
 };
-constexpr uint32_t kLayoutAlign = 2048;
+constexpr uint32_t kLayoutAlign = 1024;
 #if defined(__CUDACC__)
 __host__
 #endif
-LLC_HD Layout make_layout(int row_elems, uint32_t base) {   // row_elems = tile width * channels; base = first usable address
+LLC_HD Layout make_layout(int row_elems, uint32_t base, int warp = 0, int n_warps = 1) {   // row_elems = tile width * channels
     Layout L;
     L.ent = (base + kLayoutAlign - 1) & ~(kLayoutAlign - 1);
     L.q11 = L.ent + 128 * 8;                     // 128-byte tables on multiples of 128
     L.q5 = L.q11 + 2 * kQC;
-    L.ring = L.ent + kLayoutAlign;
-    L.bufA = L.ring + kRingBytes;
+    const uint32_t rings = L.ent + 2 * kLayoutAlign;
+    L.ring = rings + (uint32_t)warp * kRingBytes;
     const uint32_t row_bytes = (uint32_t)((row_elems + 4 + 7) & ~7) * 2;   // + one pixel of padding (read ahead)
+    const uint32_t rows = rings + (uint32_t)n_warps * kRingBytes;
+    L.bufA = rows + (uint32_t)warp * 2 * row_bytes;
     L.bufB = L.bufA + row_bytes;
-    L.end = L.bufB + row_bytes;
+    L.end = rows + (uint32_t)n_warps * 2 * row_bytes;
     return L;
 }
 // bytes to reserve when the base address is only known to be 16-byte aligned
 #if defined(__CUDACC__)
 __host__
 #endif
-LLC_HD uint32_t layout_bytes(int row_elems) { return make_layout(row_elems, 0).end + kLayoutAlign; }
+LLC_HD uint32_t layout_bytes(int row_elems, int n_warps = 1) { return make_layout(row_elems, 0, 0, n_warps).end + kLayoutAlign; }
 
 // ---- memory access -------------------------------------------------------------------------------------------
 // Device: volatile PTX on 32-bit shared-window addresses.  Volatile keeps a load where it is written (a table request at
@@ -570,8 +575,8 @@ struct Chain {
 template <int CT, bool kGlobal, int kV = 0, class Sync>
 LLC_HD bool decode_slice_rows(const Smem& m, const Layout& L, const StateMem<kGlobal>& state, const uint32_t* entry,
                               const uint8_t* src, uint32_t len, int w, int h, uint8_t* dst, size_t pitch, int lane, int nl,
-                              Sync sync) {
-    fill_tables(m, L, entry, lane, nl);
+                              Sync sync, bool tables_ready = false) {
+    if (!tables_ready) fill_tables(m, L, entry, lane, nl);     // (a CTA of several warps fills them once, before)
     uint32_t filled = ring_refill(m, L, src, len, 0, 0, lane, nl);
     sync();
     Chain<CT, kGlobal, kV> c;

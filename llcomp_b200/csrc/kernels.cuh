@@ -97,7 +97,8 @@ cudaError_t configure_slice_decoder();
 uint64_t decoder_line_scratch_bytes(const Geom& g);
 // K5, default form for 1..4 channels (decoder_chain.cu): d_gstate != nullptr -> state rows there (zeroed by the caller)
 cudaError_t launch_slice_decoder_chain(const uint8_t* d_payload, const uint64_t* d_offsets, const Geom& g,
-                                       uint8_t* d_pixels, uint8_t* d_gstate, int* d_status, cudaStream_t st);
+                                       uint8_t* d_pixels, uint8_t* d_gstate, int* d_status, cudaStream_t st,
+                                       bool shared_launch = false);
 int chain_decoder_smem_bytes(const Geom& g, bool global_state);
 
 }  // namespace llc
