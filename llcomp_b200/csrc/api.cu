@@ -31,6 +31,8 @@ void reload_switches() {
     s.frontend_tiled = on("LLCOMP_FRONTEND_TILED");
     s.decoder_simple = on("LLCOMP_DECODER_SIMPLE");
     s.decoder_v1 = on("LLCOMP_DECODER_V1");
+    s.coder_max_carveout = on("LLCOMP_CODER_MAX_CARVEOUT");
+    s.decoder_max_carveout = on("LLCOMP_DECODER_MAX_CARVEOUT");
     s.coder_split = on("LLCOMP_CODER_SPLIT");
     s.decoder_smem_state = on("LLCOMP_DECODER_SMEM_STATE");
     s.model_smem_state = on("LLCOMP_MODEL_SMEM_STATE");

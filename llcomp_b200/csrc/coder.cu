@@ -1139,6 +1139,14 @@ static cudaError_t launch_fused_from(const uint32_t* d_sym, const uint8_t* d_pix
     constexpr int kSmem = fused_smem_bytes(NS, kGlobalState, kPixels);
     const cudaError_t configured = ensure_dynamic_smem<k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels>>(kSmem);
     if (configured != cudaSuccess) return configured;
+    // Shared memory / L1 split: a kernel that has opted in to large dynamic shared memory gets the largest carve-out by
+    // default (233 KB, ~20 KB of L1); one CTA per SM needs kSmem, the rest is better spent on the state rows' L1.
+    if (kSolo && kGlobalState) {
+        const int pct = switches().coder_max_carveout ? (int)cudaSharedmemCarveoutMaxShared
+                                                      : std::min(100, ((kSmem + 2048) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        (void)cudaFuncSetAttribute(k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        (void)cudaGetLastError();                            // a hint: never fails a launch
+    }
     k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels><<<(n + NS - 1) / NS, 32 * fused_warps(NS, kSolo), kSmem, st>>>(
         d_sym, d_pixels, g, d_scratch, d_slice_bytes, d_status, gs, n);
     return cudaGetLastError();

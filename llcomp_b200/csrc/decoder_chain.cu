@@ -77,7 +77,23 @@ static cudaError_t launch_chain(const uint8_t* d_payload, const uint64_t* d_offs
     const int smem = (int)dchain::layout_bytes(std::min(g.tw, g.W) * g.C, warps) + (kGlobalState ? 0 : kStateBytes);
     const cudaError_t configured = ensure_dynamic_smem<k_slice_decoder_chain<CT, kGlobalState, kV>>(226 * 1024);
     if (configured != cudaSuccess) return configured;
-    k_slice_decoder_chain<CT, kGlobalState, kV><<<(n + warps - 1) / warps, 32 * warps, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, gs, n);
+    // Shared memory / L1 split.  Left to itself the driver gives a kernel that has opted in to large dynamic shared memory
+    // the largest carve-out (233 KB: ncu launch__shared_mem_config_size), i.e. ~20 KB of L1 -- and the chain's speed
+    // follows the L1 hit rate of its state rows.  Ask for what the resident CTAs need and no more.
+    const unsigned ctas = (n + warps - 1) / warps;
+    if (!switches().decoder_max_carveout) {
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+        const int by_smem = std::max(1, (228 * 1024) / (smem + 1024 + 16));
+        const int per_sm = std::min<int>(by_smem, std::max<int>(1, (int)((ctas * (shared_launch ? 2u : 1u) + sms - 1) / sms)));
+        const int pct = std::min(100, (per_sm * (smem + 1024 + 16) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        (void)cudaFuncSetAttribute(k_slice_decoder_chain<CT, kGlobalState, kV>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        (void)cudaGetLastError();                            // a hint: never fails a launch
+    } else {
+        (void)cudaFuncSetAttribute(k_slice_decoder_chain<CT, kGlobalState, kV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        (void)cudaGetLastError();
+    }
+    k_slice_decoder_chain<CT, kGlobalState, kV><<<ctas, 32 * warps, smem, st>>>(d_payload, d_offsets, g, d_pixels, d_status, gs, n);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,8 @@ struct Switches {
     bool model_smem_state = false;    // LLCOMP_MODEL_SMEM_STATE
     bool coder_records = false;       // LLCOMP_CODER_RECORDS     fused coder always reads K1's record array
     bool coder_pixels = false;        // LLCOMP_CODER_PIXELS      fused coder always computes its records from the pixels
+    bool decoder_max_carveout = false; // LLCOMP_DECODER_MAX_CARVEOUT  chain decoder with the largest shared-memory carve-out (least L1), for measurements
+    bool coder_max_carveout = false;  // LLCOMP_CODER_MAX_CARVEOUT  fused coder with the largest shared-memory carve-out (least L1), for measurements
     int frontend_variant = 0;         // LLCOMP_FRONTEND_VARIANT  measurement variants of the streaming front end (frontend_rows.cu)
     int decoder_variant = 0;          // LLCOMP_DECODER_VARIANT   measurement variants of the chain decoder (decoder_chain.cu)
     int fused_ns = 0;                 // LLCOMP_FUSED_NS          slices per coder CTA; 0 = automatic
