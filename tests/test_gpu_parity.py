@@ -412,7 +412,8 @@ def test_decoder_forms_agree_on_many_slices(codec):
         codec.finish()
         assert torch.equal(out.view(imgs.shape), d_px), (c, noise)
         for env in ({"LLCOMP_DECODER_SMEM_STATE": 1}, {"LLCOMP_DECODER_V1": 1}, {"LLCOMP_DECODER_SIMPLE": 1},
-                    {"LLCOMP_DECODER_VARIANT": 1}, {"LLCOMP_DECODER_VARIANT": 2}, {"LLCOMP_DECODER_VARIANT": 3}):
+                    {"LLCOMP_DECODER_VARIANT": 1}, {"LLCOMP_DECODER_VARIANT": 2}, {"LLCOMP_DECODER_VARIANT": 4},
+                    {"LLCOMP_DECODER_MAX_CARVEOUT": 1}):
             with switched(codec, **env):
                 out2 = codec.decode_device(payload, offsets, g)
                 codec.finish()
