@@ -94,6 +94,11 @@ int llcomp_b200_encode_batch(llcomp_ctx *ctx, const uint8_t *pixels, const llcom
 int llcomp_b200_decode_batch(llcomp_ctx *ctx, const uint8_t *streams, const uint64_t *offsets, int n_images,
                              uint8_t *pixels_out, uint64_t pixels_cap, llcomp_geometry *g_out);
 void llcomp_b200_free(void *p);
+/* Page-locked host memory for the buffers of the batch calls (pixels in, streams out and back): copies from and to it
+ * run asynchronously at full PCIe speed and overlap with the coding of other image groups; with pageable memory the
+ * driver stages every copy.  NULL when it cannot be had (the caller falls back to ordinary memory). */
+void *llcomp_b200_host_alloc(size_t bytes);
+void llcomp_b200_host_free(void *p);
 
 /* ---- several GPUs of one box ---------------- */
 /* Slices share nothing, so the work is dealt to the devices in contiguous blocks with no exchange between them:

@@ -43,6 +43,8 @@ SIGNATURES = {
     "llcomp_b200_encode_batch": (C.c_int, [_vp, _vp, C.POINTER(Geometry), _vp, C.c_uint64, _vp]),
     "llcomp_b200_decode_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_uint64, C.POINTER(Geometry)]),
     "llcomp_b200_free": (None, [_vp]),
+    "llcomp_b200_host_alloc": (_vp, [C.c_size_t]),
+    "llcomp_b200_host_free": (None, [_vp]),
     "llcomp_b200_encode_device": (C.c_int, [_vp, _vp, C.POINTER(Geometry), _vp, C.c_uint64, _vp, _vp]),
     "llcomp_b200_decode_device": (C.c_int, [_vp, _vp, _vp, C.POINTER(Geometry), _vp, _vp]),
     "llcomp_b200_finish": (C.c_int, [_vp, _vp]),

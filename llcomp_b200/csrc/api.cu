@@ -765,6 +765,18 @@ int llcomp_b200_decode(llcomp_ctx* ctx, const uint8_t* stream, size_t n, uint8_t
 
 void llcomp_b200_free(void* p) { free(p); }
 
+void* llcomp_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void llcomp_b200_host_free(void* p) {
+    if (p) (void)cudaFreeHost(p);
+}
+
 // Model table entry s: P | next_mps<<8 | next_lps<<16 (tests compare it with the oracle's tables).
 uint32_t llcomp_b200_debug_table(int s) {
     static const ModelTables t = make_tables();

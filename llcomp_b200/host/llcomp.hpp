@@ -14,7 +14,10 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -73,6 +76,30 @@ inline llcomp_multi* multi_context(const std::vector<int>& devices) {
     cache.emplace_back(devices, std::unique_ptr<llcomp_multi, MultiDeleter>(m));
     return m;
 }
+
+// Staging memory of the batch calls: page-locked when it can be had (llcomp_b200_host_alloc), so that the library's
+// copies run asynchronously and overlap with the coding of other image groups; ordinary memory otherwise.
+struct HostBuffer {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    bool pinned = false;
+    explicit HostBuffer(size_t bytes) : n(bytes) {
+        if (bytes == 0) return;
+        p = static_cast<uint8_t*>(llcomp_b200_host_alloc(bytes));
+        pinned = p != nullptr;
+        if (!p) p = static_cast<uint8_t*>(std::malloc(bytes));
+        if (!p) throw std::bad_alloc();
+    }
+    ~HostBuffer() {
+        if (pinned) llcomp_b200_host_free(p);
+        else std::free(p);
+    }
+    HostBuffer(const HostBuffer&) = delete;
+    HostBuffer& operator=(const HostBuffer&) = delete;
+    uint8_t* data() { return p; }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+};
 
 // RawImage carries 16-bit dimensions (llcomp.hpp:454-459); the reference truncates larger ones silently
 // (SURVEY.md defect D3), this refuses them.
@@ -146,25 +173,30 @@ inline RawImage decompressImage(const std::vector<uint8_t>& data, const Options&
 
 inline RawImage decompressImage(const std::vector<uint8_t>& data) { return decompressImage(data, Options{}); }
 
-// n equally sized images, pixels back to back -> one complete stream per image.
-inline std::vector<std::vector<uint8_t>> compressBatch(const std::vector<uint8_t>& pixels, int n_images, int width,
+// n equally sized images, pixels back to back -> one complete stream per image.  `pixels` may be any host memory; the
+// tools stage theirs in a detail::HostBuffer (page-locked).  The streams come back through a page-locked buffer.
+inline std::vector<std::vector<uint8_t>> compressBatch(const uint8_t* pixels, size_t n_bytes, int n_images, int width,
                                                        int height, int channels, const Options& opt = Options{}) {
     llcomp_geometry g{width, height, channels, opt.tile_w, opt.tile_h, n_images};
-    if (pixels.size() != llcomp_b200_sample_count(&g)) throw std::invalid_argument("llcomp: batch size mismatch");
-    std::vector<uint8_t> buf(llcomp_b200_stream_bound(&g));
+    if (n_bytes != llcomp_b200_sample_count(&g)) throw std::invalid_argument("llcomp: batch size mismatch");
+    detail::HostBuffer buf(llcomp_b200_stream_bound(&g));
     std::vector<uint64_t> off(n_images + 1);
     if (opt.devices.size() >= 2) {
         llcomp_multi* m = detail::multi_context(opt.devices);
-        const int rc = llcomp_b200_multi_encode_batch(m, pixels.data(), &g, buf.data(), buf.size(), off.data());
+        const int rc = llcomp_b200_multi_encode_batch(m, pixels, &g, buf.data(), buf.size(), off.data());
         if (rc != LLCOMP_OK) detail::raise(llcomp_b200_multi_ctx(m, 0), rc);
     } else {
         llcomp_ctx* c = detail::context(opt.device);
-        const int rc = llcomp_b200_encode_batch(c, pixels.data(), &g, buf.data(), buf.size(), off.data());
+        const int rc = llcomp_b200_encode_batch(c, pixels, &g, buf.data(), buf.size(), off.data());
         if (rc != LLCOMP_OK) detail::raise(c, rc);
     }
     std::vector<std::vector<uint8_t>> out(n_images);
-    for (int k = 0; k < n_images; ++k) out[k].assign(buf.begin() + off[k], buf.begin() + off[k + 1]);
+    for (int k = 0; k < n_images; ++k) out[k].assign(buf.data() + off[k], buf.data() + off[k + 1]);
     return out;
+}
+inline std::vector<std::vector<uint8_t>> compressBatch(const std::vector<uint8_t>& pixels, int n_images, int width,
+                                                       int height, int channels, const Options& opt = Options{}) {
+    return compressBatch(pixels.data(), pixels.size(), n_images, width, height, channels, opt);
 }
 
 // Inverse: n complete streams of the same geometry (same header, same tile grid) -> n images in one call.
@@ -177,13 +209,12 @@ inline std::vector<RawImage> decompressBatch(const std::vector<std::vector<uint8
     int rc = llcomp_b200_peek(streams[0].data(), streams[0].size(), &w, &h, &ch, &tw, &th);
     if (rc != LLCOMP_OK) detail::raise(c, rc);
     detail::check_u16(w, h);
-    std::vector<uint8_t> cat;
     std::vector<uint64_t> off(streams.size() + 1, 0);
     for (size_t k = 0; k < streams.size(); ++k) off[k + 1] = off[k] + streams[k].size();
-    cat.reserve(off.back());
-    for (const auto& s : streams) cat.insert(cat.end(), s.begin(), s.end());
+    detail::HostBuffer cat(off.back());                      // page-locked staging: streams in, pixels out
+    for (size_t k = 0; k < streams.size(); ++k) std::memcpy(cat.data() + off[k], streams[k].data(), streams[k].size());
     const size_t per_image = (size_t)w * h * ch;
-    std::vector<uint8_t> px(per_image * streams.size());
+    detail::HostBuffer px(per_image * streams.size());
     llcomp_geometry g{};
     if (opt.devices.size() >= 2)
         rc = llcomp_b200_multi_decode_batch(detail::multi_context(opt.devices), cat.data(), off.data(), (int)streams.size(),
@@ -193,7 +224,7 @@ inline std::vector<RawImage> decompressBatch(const std::vector<std::vector<uint8
     if (rc != LLCOMP_OK) detail::raise(c, rc);
     out.reserve(streams.size());
     for (size_t k = 0; k < streams.size(); ++k)
-        out.push_back(RawImage{std::vector<uint8_t>(px.begin() + k * per_image, px.begin() + (k + 1) * per_image),
+        out.push_back(RawImage{std::vector<uint8_t>(px.data() + k * per_image, px.data() + (k + 1) * per_image),
                                (uint16_t)w, (uint16_t)h, (uint8_t)ch});
     return out;
 }

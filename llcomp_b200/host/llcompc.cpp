@@ -73,11 +73,14 @@ int main(int argc, char** argv) {
                                                                   imgs[k].channels, opt)))
                     return 1;
             } else {
-                std::vector<uint8_t> all;
-                all.reserve(imgs[k].pixels.size() * (e - k));
-                for (size_t i = k; i < e; ++i) all.insert(all.end(), imgs[i].pixels.begin(), imgs[i].pixels.end());
-                const auto streams = llcomp::compressBatch(all, (int)(e - k), imgs[k].width, imgs[k].height,
-                                                           imgs[k].channels, opt);
+                const size_t per_image = imgs[k].pixels.size();
+                llcomp::detail::HostBuffer all(per_image * (e - k));     // page-locked: the upload overlaps with the coding
+                for (size_t i = k; i < e; ++i) {
+                    std::memcpy(all.data() + (i - k) * per_image, imgs[i].pixels.data(), per_image);
+                    std::vector<uint8_t>().swap(imgs[i].pixels);          // the staged copy is the only one kept
+                }
+                const auto streams = llcomp::compressBatch(all.data(), all.size(), (int)(e - k), imgs[k].width,
+                                                           imgs[k].height, imgs[k].channels, opt);
                 for (size_t i = k; i < e; ++i)
                     if (!write_stream(files[i], streams[i - k])) return 1;
             }
