@@ -15,7 +15,7 @@ __constant__ ModelTables c_tables_chain = make_tables();
 // shared memory in front of the chain's buffers.  After the tables are filled the warps never meet again.
 constexpr int kChainMaxWarps = 7;
 template <int CT, bool kGlobalState, int kV>
-__global__ void __launch_bounds__(32 * kChainMaxWarps) k_slice_decoder_chain(const uint8_t* __restrict__ payload,
+__global__ void __launch_bounds__(32 * kChainMaxWarps, 1) k_slice_decoder_chain(const uint8_t* __restrict__ payload,
                                                                              const uint64_t* __restrict__ offsets, Geom g,
                                                                              uint8_t* __restrict__ pixels,
                                                                              int* __restrict__ status,

@@ -278,7 +278,7 @@ struct Chain {
     int l[CT], t[CT];                // left neighbour; top neighbour (becomes the next sample's tl)
     int pred[CT], pre[CT];           // median prediction; hash part from the rows above
     int q11v[CT], q5v[CT];           // q11(l - tl), q5(L - l), requested in part 1
-    int nhash[CT];                   // signed context hash (part 2)
+    int nhash[CT], nah[CT];          // signed context hash and its magnitude (part 2)
     Row nrow[CT];                    // its state row as requested in part 2
     int whash[CT];                   // |hash| and row the plane wrote back last (forwarding)
     Row wrow[CT];
@@ -334,7 +334,8 @@ struct Chain {
     LLC_HD void part2(int i, uint32_t after = 0) {
         const int hsh = pre[i] + q11v[i] + 605 * q5v[i] + (int)after;
         nhash[i] = hsh;
-        nrow[i] = st.load((uint32_t)iabs(hsh));
+        nah[i] = iabs(hsh);
+        nrow[i] = st.load((uint32_t)nah[i]);
     }
 
     // Start of row h: every plane's first sample.  First column: l = L = tl = t (h > 0) or 128 (h == 0).
@@ -541,12 +542,14 @@ struct Chain {
                 if (CT == 1) part2(0);
                 // ---- [A] the row as requested, or as rewritten since; table entries; operands of the sample after
                 const int hsh = nhash[i];
-                const int ah = iabs(hsh);
-                Row row = nrow[i];
+                const int ah = nah[i];
+                Row& row = wrow[i];                                      // the plane's "last written" row is the working copy
+                row = nrow[i];
                 for (int k = CT - 1; k >= 1; --k) {                      // k samples ago; newest last
                     const int p = (i + CT - k) % CT;
                     if (ah == whash[p]) row = wrow[p];
                 }
+                whash[i] = ah;                                           // (only the other planes compare against it)
                 const Ent e0 = ent_of(row.x, 0), e1 = ent_of(row.x, 1), e2 = ent_of(row.x, 2), e3 = ent_of(row.x, 3);
                 const Ent e5 = ent_of(row.y, 1), e6 = ent_of(row.y, 2), e7 = ent_of(row.y, 3);
                 const int t_next = kFirstRow ? 0 : m.s16(aA + 2u * (CT + i));
@@ -559,7 +562,6 @@ struct Chain {
                                     : residual_with(row, e0, e1, e2, e3, e5, e6, e7);
                 // ---- [D] write back, reconstruct, part 1 of the plane's next sample
                 st.store((uint32_t)ah, row);
-                whash[i] = ah; wrow[i] = row;
                 const int cur = (int)(int16_t)(pr + (hsh < 0 ? -diff : diff));   // llcomp.hpp:526-529
                 m.st16(aB + 2u * i, cur);
                 part1<kFirstRow>(i, cur, w == 0 ? cur : left, t_next, p_next);   // w == 0: the next sample's L = l (:496)
