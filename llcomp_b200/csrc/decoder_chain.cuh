@@ -358,7 +358,8 @@ struct Chain {
         const uint32_t r0 = tq >> 8, t0 = tq & ~0xFFu;
         const bool bit = cS >= tq;                                      // low >= range - r1, llcomp.hpp:110
         R = bit ? R - r0 : r0;
-        cS = bit ? cS - t0 : cS;
+        const uint32_t cd = cS - t0;                                    // wraps above cS exactly when the bit is 0
+        cS = cd < cS ? cd : cS;                                         // (cS >= tq <=> cS >= t0: the low byte of cS is 0xFF)
         constexpr uint32_t s0 = kB == 0 ? 0x3214u : kB == 1 ? 0x3240u : kB == 2 ? 0x3410u : 0x4210u;
         constexpr uint32_t s1 = kB == 0 ? 0x3215u : kB == 1 ? 0x3250u : kB == 2 ? 0x3510u : 0x5210u;
         w = bperm(w, e.nx, bit ? s1 : s0);
