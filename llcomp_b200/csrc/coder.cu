@@ -802,8 +802,11 @@ constexpr int fused_smem_bytes(int ns, bool global_state, bool pixels) {
     return 1024 + ns * kFusedPerSlice + (global_state ? 0 : kRowBytesSmem) + (pixels ? ns * kRecBytes + (int)sizeof(QuantBytes) : 0);
 }
 
-template <int NS, bool kGlobalState, int kSolo, bool kPixels>
-__global__ void __launch_bounds__(32 * fused_warps(NS, kSolo)) k_slice_coder_fused(const uint32_t* __restrict__ sym,
+// kWide: the launch is one wave of one CTA per SM, so the kernel may take the registers it wants (65 instead of 64 and no
+// spill: 176.7 -> 174.7 ms on configs[3]); otherwise two CTAs must fit an SM (with more CTAs than SMs the second resident
+// CTA is worth more: 4096 slices code at 22.1 GB/s against 16.0), which caps the registers at 64.
+template <int NS, bool kGlobalState, int kSolo, bool kPixels, bool kWide = false>
+__global__ void __launch_bounds__(32 * fused_warps(NS, kSolo), kWide ? 1 : 2) k_slice_coder_fused(const uint32_t* __restrict__ sym,
                                                                        const uint8_t* __restrict__ pixels, Geom g,
                                                                        uint8_t* __restrict__ scratch,
                                                                        uint32_t* __restrict__ slice_bytes,
@@ -1143,15 +1146,20 @@ static cudaError_t launch_fused_from(const uint32_t* d_sym, const uint8_t* d_pix
     // default (233 KB, ~20 KB of L1); one CTA per SM needs kSmem, the rest is better spent on the state rows' L1.
     // (Only while the launch is one wave of one CTA per SM: with more CTAs than SMs the largest carve-out lets two of
     // them share an SM, which is worth more -- 4096 slices of 256^2: 22.1 GB/s against 15.9.)
-    if (kSolo && kGlobalState) {
-        const bool one_wave = (n + NS - 1) / NS <= (unsigned)sm_count();
-        const int pct = (switches().coder_max_carveout || !one_wave)
-                            ? (int)cudaSharedmemCarveoutMaxShared
-                            : std::min(100, ((kSmem + 2048) * 100 + 228 * 1024 - 1) / (228 * 1024));
-        (void)cudaFuncSetAttribute(k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    const bool one_wave = kSolo && kGlobalState && (n + NS - 1) / NS <= (unsigned)sm_count();
+    const dim3 grid((n + NS - 1) / NS), block(32 * fused_warps(NS, kSolo));
+    if (one_wave) {
+        constexpr auto kernel = k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels, (kSolo && kGlobalState)>;
+        const cudaError_t wide_configured = ensure_dynamic_smem<kernel>(kSmem);
+        if (wide_configured != cudaSuccess) return wide_configured;
+        const int pct = switches().coder_max_carveout ? (int)cudaSharedmemCarveoutMaxShared
+                                                      : std::min(100, ((kSmem + 2048) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         (void)cudaGetLastError();                            // a hint: never fails a launch
+        kernel<<<grid, block, kSmem, st>>>(d_sym, d_pixels, g, d_scratch, d_slice_bytes, d_status, gs, n);
+        return cudaGetLastError();
     }
-    k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels><<<(n + NS - 1) / NS, 32 * fused_warps(NS, kSolo), kSmem, st>>>(
+    k_slice_coder_fused<NS, kGlobalState, kSolo, kPixels><<<grid, block, kSmem, st>>>(
         d_sym, d_pixels, g, d_scratch, d_slice_bytes, d_status, gs, n);
     return cudaGetLastError();
 }
